@@ -1,0 +1,160 @@
+/* xee_b200.h — C-ABI of the B200-native elliptic-solve hot path of XLab-EE-fortran.
+ *
+ * The reference (meteorologytoday/XLab-EE-fortran) has NO C ABI of its own: the hot
+ * path is the Fortran module `elliptic_tools` (xtt-lib-fortran/elliptic_tools.f90),
+ * called from src/diagnose/diagnose.f90:7,15,34,42.  This header is what a
+ * `bind(C)` interface block in a replacement `module elliptic_tools` binds to
+ * (fortran/elliptic_tools.f90 in this repo; INTEGRATION.md shows the stub).
+ *
+ * Part 1 mirrors the module procedures one to one (Fortran conventions: every
+ * argument by reference, default INTEGER = 32 bit, arrays column-major and
+ * contiguous, HOST pointers, synchronous).  Part 2 is the batched device API the
+ * efficiency-map / time-series callers use (plain pointers and sizes only).
+ *
+ * All compute runs in hand-written CUDA for sm_100a.  There is no CPU fallback:
+ * every entry point fails loudly (message on stderr + non-zero status / abort for
+ * the Fortran-style void entry points) when no CUDA device is usable.
+ */
+#ifndef XEE_B200_H
+#define XEE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* elliptic_tools.f90:3-4 — public error bits of the `err` bitmask */
+#define XEE_ERR_OVER_MAX_ITERATION 1
+#define XEE_ERR_EXPLODE 2
+
+/* =====================================================================================
+ * Part 1 — drop-in for `module elliptic_tools` (+ the driver's FD post-processing)
+ * ===================================================================================== */
+
+/* cal_coe(a,b,c,workspace,dx,dy,nx,ny,err)            elliptic_tools.f90:8-60
+ * a(nx-1,ny-2) b(nx-1,ny-1) c(nx-2,ny-1) -> coe(9,nx,ny).  Only interior entries
+ * (2..nx-1, 2..ny-1) of coe are written, as in the reference.  err: 0 on return. */
+void xee_cal_coe_f32(const float* a, const float* b, const float* c, float* coe, const float* dx,
+                     const float* dy, const int* nx, const int* ny, int* err);
+void xee_cal_coe_f64(const double* a, const double* b, const double* c, double* coe, const double* dx,
+                     const double* dy, const int* nx, const int* ny, int* err);
+
+/* do_elliptic(psi,coe,outdat,nx,ny,err)               elliptic_tools.f90:64-90
+ * outdat interior = 9-point apply; boundary of outdat untouched; err = 1 on
+ * return (the reference sets it to 1 at :73 and never clears it). */
+void xee_do_elliptic_f32(const float* psi, const float* coe, float* outdat, const int* nx, const int* ny, int* err);
+void xee_do_elliptic_f64(const double* psi, const double* coe, double* outdat, const int* nx, const int* ny, int* err);
+
+/* solve_elliptic(max_iter,check_step,converge_time,lost_rate,strategy_r1,strategy_r2,
+ *                alpha,dat,coe,f,workspace,nx,ny,err,debug)   elliptic_tools.f90:93-265
+ * Weighted-Jacobi relaxation with the reference's stop-rule state machine.
+ * In/out: max_iter (sweeps used), strategy_r1 (last RMS residual), strategy_r2 (last
+ * |ratio|), dat (boundary + first guess in, solution out).  workspace: scratch, left as
+ * the reference leaves it (the other ping-pong buffer).  err: bitmask (bit 0 = max_iter
+ * hit).  Both criteria non-positive: prints the reference's message and stops the
+ * process like Fortran STOP (exit status 0), elliptic_tools.f90:126-129.
+ * Environment: XEE_ARITH=strict|fast (default strict: no FMA contraction, true division,
+ * iterates bit-identical to the reference's operation order); XEE_METHOD=jacobi|chebyshev
+ * (default jacobi, the reference's iteration). */
+void xee_solve_elliptic_f32(int* max_iter, const int* check_step, const int* converge_time, const int* lost_rate,
+                            float* strategy_r1, float* strategy_r2, const float* alpha, float* dat,
+                            const float* coe, const float* f, float* workspace, const int* nx, const int* ny,
+                            int* err, const int* debug);
+void xee_solve_elliptic_f64(int* max_iter, const int* check_step, const int* converge_time, const int* lost_rate,
+                            double* strategy_r1, double* strategy_r2, const double* alpha, double* dat,
+                            const double* coe, const double* f, double* workspace, const int* nx, const int* ny,
+                            int* err, const int* debug);
+
+/* judge_error(err)                                     elliptic_tools.f90:333-358 */
+void xee_judge_error(const int* err);
+
+/* a/b/c normalisation                                  src/diagnose/initialize-variables.f90:72-95
+ * A,B,C on O(nr,nz); rcuva(nr), rho(nz) -> a sA(nr-1,nz-2), b B(nr-1,nz-1), c sC(nr-2,nz-1) */
+void xee_build_abc_f32(const float* A, const float* B, const float* C, const float* rcuva, const float* rho,
+                       float* a, float* b, float* c, const int* nr, const int* nz);
+void xee_build_abc_f64(const double* A, const double* B, const double* C, const double* rcuva, const double* rho,
+                       double* a, double* b, double* c, const int* nr, const int* nz);
+
+/* cal_eta(rchi,eta)                                    src/diagnose/quick-tools1.f90:1-13
+ * host-associated driver variables (ra, rcuva, rho, exner) become explicit arguments. */
+void xee_cal_eta_f32(const float* rchi, float* eta, const float* ra, const float* rcuva, const float* rho,
+                     const float* exner, const int* nr, const int* nz);
+void xee_cal_eta_f64(const double* rchi, double* eta, const double* ra, const double* rcuva, const double* rho,
+                     const double* exner, const int* nr, const int* nz);
+
+/* cal_uw(from_rpsi,to_u,to_w)                          src/diagnose/quick-tools1.f90:15-41 */
+void xee_cal_uw_f32(const float* rpsi, float* u, float* w, const float* ra, const float* rcuva, const float* za,
+                    const float* rho, const int* nr, const int* nz);
+void xee_cal_uw_f64(const double* rpsi, double* u, double* w, const double* ra, const double* rcuva,
+                    const double* za, const double* rho, const int* nr, const int* nz);
+
+/* =====================================================================================
+ * Part 2 — batched device API (new; not in the reference).  Status codes: 0 = ok.
+ * ===================================================================================== */
+#define XEE_F32 0
+#define XEE_F64 1
+#define XEE_ARITH_STRICT 0 /* reference operation order, no FMA, true division          */
+#define XEE_ARITH_FAST 1   /* FMA + precomputed reciprocal (same fixed point, 1e-13 rel) */
+#define XEE_METHOD_JACOBI 0    /* the reference's weighted Jacobi                        */
+#define XEE_METHOD_CHEBYSHEV 1 /* Chebyshev-accelerated Jacobi (same residual definition)*/
+
+typedef struct xee_plan xee_plan;
+
+typedef struct xee_plan_desc {
+  int dtype;      /* XEE_F32 | XEE_F64                                                   */
+  int nx, ny;     /* grid (nr, nz); fields are [ny][nx] with i (radius) contiguous       */
+  int nbatch;     /* independent solves per call                                         */
+  int shared_coe; /* 1: one operator for the whole batch (map); 0: one per solve         */
+  int arith;      /* XEE_ARITH_*                                                         */
+  int method;     /* XEE_METHOD_*                                                        */
+  int device;     /* CUDA device ordinal, -1 = current                                   */
+  int kernel;     /* 0 = auto; >0 forces a sweep-kernel variant          */
+} xee_plan_desc;
+
+typedef struct xee_solve_params {
+  int max_iter, check_step, converge_time, lost_rate; /* as solve_elliptic's arguments  */
+  double r1, r2, alpha;                               /* r1/r2 <= 0 disables a criterion */
+  const void* r1_per_solve; /* optional DEVICE array [nbatch] of the plan's dtype         */
+  double rho_jacobi;        /* Chebyshev only: spectral-radius estimate, <=0 = estimate   */
+  int detect_explode;       /* 1: non-finite residual sets XEE_ERR_EXPLODE and stops      */
+  int sync_every;           /* host polls the active-solve count every N checks (>=1)     */
+} xee_solve_params;
+
+const char* xee_last_error(void);
+int xee_device_count(void);
+const char* xee_build_info(void);
+
+int xee_plan_create(const xee_plan_desc* desc, xee_plan** out);
+int xee_plan_destroy(xee_plan* p);
+/* Operator upload.  AoS = the reference's coe(9,nx,ny)[,nbatch] layout. */
+int xee_plan_set_coe_aos_host(xee_plan* p, const void* coe_host);
+int xee_plan_set_coe_aos_dev(xee_plan* p, const void* coe_dev);
+/* K1+K2 on device: a,b,c (device, reference shapes) -> planar operator.  Per-solve when shared_coe==0. */
+int xee_plan_set_abc_dev(xee_plan* p, const void* a_dev, const void* b_dev, const void* c_dev, double dx, double dy);
+/* Solve: psi_dev [nbatch][ny][nx] in/out (boundary + first guess in), f_dev same shape.
+ * Per-solve outputs are HOST arrays (may be NULL): iters[nbatch], r1_out/r2_out[nbatch] (double), err[nbatch]. */
+int xee_plan_solve_dev(xee_plan* p, void* psi_dev, const void* f_dev, const xee_solve_params* prm, int* iters,
+                       double* r1_out, double* r2_out, int* err, void* stream);
+/* Same with HOST psi/f (pageable or pinned): the end-to-end entry the bench's e2e leg times. */
+int xee_plan_solve_host(xee_plan* p, void* psi_host, const void* f_host, const xee_solve_params* prm, int* iters,
+                        double* r1_out, double* r2_out, int* err);
+/* Exactly `sweeps` sweeps, no stop rule (bench / fixed-sweep parity).  rms_out: HOST [nbatch] RMS residual of
+ * the last sweep, or NULL.  Result left in psi_dev. */
+int xee_plan_sweeps_dev(xee_plan* p, void* psi_dev, const void* f_dev, double alpha, int sweeps, double* rms_out,
+                        void* stream);
+/* out = L psi (interior; boundary 0) for the whole batch. */
+int xee_plan_apply_dev(xee_plan* p, const void* psi_dev, void* out_dev, void* stream);
+/* Kernel-launch counter (bench.py's gpu_launches): launches issued by this library since reset. */
+long long xee_launch_count(int reset);
+/* Time (ms, CUDA events on the plan's stream) and launches of the dominant sweep kernel since reset. */
+int xee_sweep_kernel_stats(xee_plan* p, double* ms_total, long long* launches, int reset);
+
+/* Post-processing on device fields (K5/K6), batch-wide.  geometry arrays are DEVICE pointers of the plan dtype. */
+int xee_eta_dev(int dtype, const void* rchi, void* eta, const void* ra, const void* rcuva, const void* rho,
+                const void* exner, int nr, int nz, int nbatch, void* stream);
+int xee_uw_dev(int dtype, const void* rpsi, void* u, void* w, const void* ra, const void* rcuva, const void* za,
+               const void* rho, int nr, int nz, int nbatch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEE_B200_H */

@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on the same inputs.
+
+Tolerances (north_star): streamfunction within 1e-8 relative L2, efficiency within 1e-6 relative.
+STRICT arithmetic is held to a tighter bar: iterates BIT-IDENTICAL to the oracle at fixed sweep
+counts; only the residual norm (a parallel instead of sequential sum) is compared to a tolerance.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.util import GOLDEN, golden_json, ref_test1_inputs, rel_l2, sha
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DTS = {"f32": np.float32, "f64": np.float64}
+RES_TOL = {"f32": 2e-4, "f64": 1e-12}     # residual norm: tree sum (GPU) vs sequential sum (reference)
+
+
+def _mods():
+    import torch
+    import xlab_ee_fortran_b200 as X
+    from oracle import oracle as O
+    return torch, X, O
+
+
+def _rand_case(nx, ny, dt, seed=0, bscale=0.05):
+    rng = np.random.default_rng(seed)
+    a = (1.0 + rng.random((ny - 2, nx - 1))).astype(dt); c = (1.0 + rng.random((ny - 1, nx - 2))).astype(dt)
+    b = (bscale * rng.standard_normal((ny - 1, nx - 1))).astype(dt)
+    f = rng.standard_normal((ny, nx)).astype(dt); x0 = rng.standard_normal((ny, nx)).astype(dt)
+    return a, b, c, f, x0
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shape", [(3, 3), (5, 4), (67, 35), (200, 200), (512, 256)])
+def test_cal_coe_and_do_elliptic_bitwise(name, shape):
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = shape
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=nx)
+    coe = np.full((ny, nx, 9), 7.0, dt)                    # sentinel: boundary entries must stay untouched
+    assert X.cal_coe(a, b, c, coe, 0.7, 1.3, nx, ny) == 0
+    ref, _ = O.cal_coe(a, b, c, 0.7, 1.3, nx, ny)
+    assert np.array_equal(coe[1:-1, 1:-1], ref[1:-1, 1:-1])
+    assert np.all(coe[0] == 7) and np.all(coe[-1] == 7) and np.all(coe[:, 0] == 7) and np.all(coe[:, -1] == 7)
+    out = np.full((ny, nx), 3.0, dt)
+    assert X.do_elliptic(x0, ref, out, nx, ny) == 1        # err stays 1 (elliptic_tools.f90:73)
+    oref = O.do_elliptic(x0, ref)
+    assert np.array_equal(out[1:-1, 1:-1], oref[1:-1, 1:-1])
+    assert np.all(out[0] == 3) and np.all(out[:, 0] == 3)
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shape,sweeps,alpha", [((3, 3), 5, 1.0), ((34, 19), 37, 0.8), ((130, 70), 200, 1.0), ((512, 256), 101, 0.95)])
+def test_fixed_sweeps_bitwise(name, shape, sweeps, alpha):
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = shape
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=sweeps)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    dat = x0.copy(); wk = np.zeros_like(dat)
+    it, r1, r2, err = X.solve_elliptic(sweeps, 10, 10, 5, 1e-30, 1.0, alpha, dat, coe, f, wk, nx, ny)
+    ref = O.solve_elliptic(sweeps, 10, 10, 5, 1e-30, 1.0, alpha, x0, coe, f)
+    assert (it, err) == (ref["max_iter"], ref["err"]) == (sweeps, 1)
+    assert np.array_equal(dat, ref["dat"])
+    assert np.array_equal(wk, ref["workspace"])            # the other ping-pong buffer, as the reference leaves it
+    assert r1 == pytest.approx(ref["r1"], rel=RES_TOL[name])
+    assert r2 == pytest.approx(ref["r2"], rel=1e-3, abs=1e-6)
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+def test_stop_rule_r1_decides(name):
+    """Parity protocol (b): cases where r1 alone decides - sweep count, err and field must match exactly."""
+    torch, X, O = _mods()
+    dt = DTS[name]
+    z = np.load(os.path.join(GOLDEN, f"small_{name}.npz"))
+    ny, nx = z["A"].shape
+    coe = z["coe"]; f = z["f"].astype(dt); bc = z["bc"].astype(dt)
+    dat = bc.copy(); wk = np.zeros_like(dat)
+    it, r1, r2, err = X.solve_elliptic(200000, 50, 4, 3, float(z["r1_in"]), 2.0, 0.8, dat, coe, f, wk, nx, ny)
+    assert (it, err) == (int(z["stop_sweeps"]), 0)
+    assert np.array_equal(dat, z["psi_stop"])              # golden from the numpy restatement, bit for bit
+    assert r1 == pytest.approx(float(z["stop_r1"]), rel=RES_TOL[name])
+    # 50 sweeps, golden field
+    dat = bc.copy()
+    it, r1, r2, err = X.solve_elliptic(50, 10, 3, 2, 1e-30, 1.0, 0.8, dat, coe, f, wk, nx, ny)
+    assert np.array_equal(dat, z["psi50"]) and (it, err) == (50, 1)
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+def test_test1_reference_case_through_dropin(name):
+    """BASELINE config 1: test/test1 (200x200, BAROTROPIC, r1=r2=5e-3) through cal_coe + solve_elliptic + cal_eta."""
+    torch, X, O = _mods()
+    dt = DTS[name]
+    gold = golden_json()["test1"][name]
+    A, B, C, bc = ref_test1_inputs()
+    d = O.Domain((0.0, 1.0), (0.0, 1.0), 200, 200, 0, 0)
+    g = O.geometry(d, dt)
+    a, b, c = O.build_abc(A.astype(dt), B.astype(dt), C.astype(dt), d)
+    coe = np.zeros((200, 200, 9), dt)
+    X.cal_coe(a, np.zeros_like(b), c, coe, g["dr"], g["dz"], 200, 200)
+    assert sha(coe) == gold["coe_sha256"]
+    f = -(B.astype(dt))
+    for sweeps, key in ((100, "psi100_sha256"), (1000, "psi1000_sha256")):
+        dat = bc.astype(dt).copy(); wk = np.zeros_like(dat)
+        X.solve_elliptic(sweeps, 100, 10, 5, 5e-3, 5e-3, 1.0, dat, coe, f, wk, 200, 200)
+        assert sha(dat) == gold[key]
+    # run to the stop rule: the stop sweep sits on the round-off floor, so report counts
+    # side by side and assert the converged FIELD and eta, not the sweep count.
+    dat = bc.astype(dt).copy(); wk = np.zeros_like(dat)
+    it, r1, r2, err = X.solve_elliptic(100000, 100, 10, 5, 5e-3, 5e-3, 1.0, dat, coe, f, wk, 200, 200)
+    ref = O.solve_elliptic(100000, 100, 10, 5, 5e-3, 5e-3, 1.0, bc.astype(dt), coe, f)
+    print(f"test1 {name}: GPU stop sweep {it}, oracle {ref['max_iter']}, r1 {r1:.3e} vs {ref['r1']:.3e}")
+    assert err == 0 and ref["err"] == 0
+    tol = 1e-8 if name == "f64" else 2e-4
+    assert rel_l2(dat, ref["dat"]) < tol
+    eta = np.zeros((200, 199), dt)
+    import ctypes as C
+    X._lib.lib().xee_cal_eta_f64 if name == "f64" else None
+    fn = getattr(X._lib.lib(), f"xee_cal_eta_{name}"); fn.restype = None
+    p = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    fn(p(dat), p(eta), p(g["ra"]), p(g["rcuva"]), p(g["rho"]), p(g["exner"]), C.byref(C.c_int(200)), C.byref(C.c_int(200)))
+    assert np.array_equal(eta, O.cal_eta(dat, d))          # K5 bitwise on the same input
+    assert float(eta.max()) == pytest.approx(gold["eta_stop_max"], rel=1e-6 if name == "f64" else 1e-3)
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shared", [True, False])
+def test_batched_plan_matches_oracle_bitwise(name, shared):
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny, nb = 70, 45, 11
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=3)
+    rng = np.random.default_rng(9)
+    F = np.stack([f * dt(k + 1) for k in range(nb)]); P = np.stack([x0 * dt(0.5 * k) for k in range(nb)])
+    if shared:
+        coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    else:
+        coe = np.stack([O.cal_coe(a * dt(1 + 0.1 * k), b, c, 1.0, 0.5, nx, ny)[0] for k in range(nb)])
+    plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=shared, arith="strict")
+    plan.set_coe_aos(coe)
+    psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+    # different RHS scales finish at different checks: exercises per-solve done flags
+    rms_f = float(np.sqrt((F[0][1:-1, 1:-1].astype(np.float64) ** 2).mean()))
+    prm = X.SolveParams(max_iter=4000, check_step=20, converge_time=2, lost_rate=5, r1=2e-3 * rms_f if name == "f64" else 2e-2 * rms_f, r2=0.0, alpha=0.9)
+    out = plan.solve(psi, ft, prm)
+    rb = O.solve_batch(4000, 20, 2, 5, prm.r1, 0.0, 0.9, P, coe, F, threads=4)
+    assert list(out["iters"]) == list(rb["max_iter"]) and list(out["err"]) == list(rb["err"])
+    assert len(set(out["iters"])) > 1
+    assert np.array_equal(psi.cpu().numpy(), rb["dat"])
+    assert np.allclose(out["r1"], rb["r1"], rtol=RES_TOL[name])
+    # apply == do_elliptic for the batch
+    Lp = plan.apply(torch.from_numpy(P).cuda()).cpu().numpy()
+    for k in range(nb):
+        assert np.array_equal(Lp[k], O.do_elliptic(P[k], coe if shared else coe[k]))
+
+
+def test_set_abc_on_device_matches_cal_coe():
+    torch, X, O = _mods()
+    nx, ny = 90, 50
+    a, b, c, f, x0 = _rand_case(nx, ny, np.float64, seed=5)
+    coe, _ = O.cal_coe(a, b, c, 0.3, 0.9, nx, ny)
+    p1 = X.Plan(nx, ny, 1, "f64"); p1.set_coe_aos(coe)
+    p2 = X.Plan(nx, ny, 1, "f64"); p2.set_abc(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda(), 0.3, 0.9)
+    x = torch.from_numpy(x0[None]).cuda()
+    assert torch.equal(p1.apply(x), p2.apply(x))
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+def test_fast_arithmetic_within_tolerance(name):
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = 128, 96
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=11)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 1.0, nx, ny)
+    plan = X.Plan(nx, ny, 1, name, arith="fast"); plan.set_coe_aos(coe)
+    psi = torch.from_numpy(x0[None].copy()).cuda(); ft = torch.from_numpy(f[None].copy()).cuda()
+    rms = plan.sweeps(psi, ft, 1.0, 500, want_rms=True)
+    ref = O.solve_elliptic(500, 500, 10, 5, 1e-30, 1.0, 1.0, x0, coe, f)
+    assert rel_l2(psi.cpu().numpy()[0], ref["dat"]) < (1e-12 if name == "f64" else 1e-4)
+    assert rms[0] == pytest.approx(ref["r1"], rel=1e-9 if name == "f64" else 1e-3)
+
+
+def test_chebyshev_reaches_the_same_solution():
+    """Accelerated mode: same discretisation, same residual definition, iterated to the same tolerance."""
+    torch, X, O = _mods()
+    nx, ny = 160, 96
+    a, b, c, f, x0 = _rand_case(nx, ny, np.float64, seed=13, bscale=0.02)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 1.0, nx, ny)
+    rms_f = float(np.sqrt((f[1:-1, 1:-1] ** 2).mean()))
+    r1 = 1e-12 * rms_f
+    ref = O.solve_elliptic(400000, 100, 3, 5, r1, 0.0, 1.0, x0, coe, f)
+    assert ref["err"] == 0
+    plan = X.Plan(nx, ny, 1, "f64", arith="fast", method="chebyshev"); plan.set_coe_aos(coe)
+    psi = torch.from_numpy(x0[None].copy()).cuda(); ft = torch.from_numpy(f[None].copy()).cuda()
+    out = plan.solve(psi, ft, X.SolveParams(max_iter=400000, check_step=100, converge_time=3, r1=r1, r2=0.0, alpha=1.0))
+    print("chebyshev sweeps", out["iters"][0], "jacobi sweeps", ref["max_iter"])
+    assert out["err"][0] == 0 and out["r1"][0] < r1
+    assert out["iters"][0] * 5 < ref["max_iter"]
+    assert rel_l2(psi.cpu().numpy()[0], ref["dat"]) < 1e-8
+
+
+def test_uw_kernels_bitwise():
+    torch, X, O = _mods()
+    import ctypes as C
+    for name, dt in DTS.items():
+        d = O.Domain((0.0, 3.0e5), (0.0, 1.0e4), 75, 41, 0, 0)
+        g = O.geometry(d, dt)
+        rpsi = np.random.default_rng(2).standard_normal((41, 75)).astype(dt)
+        u = np.zeros((40, 75), dt); w = np.zeros((41, 74), dt)
+        fn = getattr(X._lib.lib(), f"xee_cal_uw_{name}"); fn.restype = None
+        p = lambda arr: arr.ctypes.data_as(C.c_void_p)
+        fn(p(rpsi), p(u), p(w), p(g["ra"]), p(g["rcuva"]), p(g["za"]), p(g["rho"]), C.byref(C.c_int(75)), C.byref(C.c_int(41)))
+        uo, wo = O.cal_uw(rpsi, d)
+        assert np.array_equal(u, uo) and np.array_equal(w, wo)
+        assert np.all(u[:, 0] == 0)                        # ra(1) == 0 -> u = 0 (quick-tools1.f90:33-37)
+        A = np.random.default_rng(3).random((41, 75)).astype(dt)
+        a = np.zeros((39, 74), dt); b = np.zeros((40, 74), dt); c = np.zeros((40, 73), dt)
+        fn = getattr(X._lib.lib(), f"xee_build_abc_{name}"); fn.restype = None
+        fn(p(A), p(A * 2), p(A + 1), p(g["rcuva"]), p(g["rho"]), p(a), p(b), p(c), C.byref(C.c_int(75)), C.byref(C.c_int(41)))
+        ao, bo, co = O.build_abc(A, A * 2, A + 1, d)
+        assert np.array_equal(a, ao) and np.array_equal(b, bo) and np.array_equal(c, co)
+
+
+def test_fortran_stop_behaviour_in_the_c_abi():
+    """Both criteria non-positive inside the C entry point: message on stdout, process exits 0 (Fortran STOP)."""
+    code = ("import ctypes as C, numpy as np\n"
+            "from xlab_ee_fortran_b200 import _lib\n"
+            "L=_lib.lib(); z=np.zeros((4,4)); c=np.zeros((4,4,9)); p=lambda a:a.ctypes.data_as(C.c_void_p)\n"
+            "i=lambda v:C.byref(C.c_int(v)); d=lambda v:C.byref(C.c_double(v))\n"
+            "L.xee_solve_elliptic_f64(i(10),i(1),i(1),i(1),d(0.0),d(-1.0),d(1.0),p(z),p(c),p(z),p(z.copy()),i(4),i(4),i(0),i(0))\n"
+            "print('NOT REACHED')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "cannot both be non-positive" in r.stdout and "NOT REACHED" not in r.stdout
+
+
+def test_debug_prints_match_reference_format(capfd):
+    torch, X, O = _mods()
+    nx, ny = 20, 16
+    a, b, c, f, x0 = _rand_case(nx, ny, np.float64, seed=1)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 1.0, nx, ny)
+    dat = x0.copy(); wk = np.zeros_like(dat)
+    X.solve_elliptic(30, 10, 10, 5, 1e-30, 1.0, 1.0, dat, coe, f, wk, nx, ny, debug=2)
+    out = capfd.readouterr().out
+    assert " ----- Solve Elliptic Inputs -----" in out
+    assert out.count("Iter: ") == 3 and "Iter:       10, err_now: " in out
+    assert " Elliptic Tools: [Error] Max iteration reached." in out
