@@ -154,6 +154,38 @@ int xee_eta_dev(int dtype, const void* rchi, void* eta, const void* ra, const vo
 int xee_uw_dev(int dtype, const void* rpsi, void* u, void* w, const void* ra, const void* rcuva, const void* za,
                const void* rho, int nr, int nz, int nbatch, void* stream);
 
+/* =====================================================================================
+ * Part 3 - efficiency map: one vortex (A,B,C), one elliptic solve per heating location.
+ * Restates the heating -> secondary circulation -> kinetic-energy generation -> efficiency
+ * chain of src/old-diagnose/diagnose.f90 (:383-406 source term, :449-461 solve, :915-941 w,
+ * :1117-1127 w*theta, :1029-1113 integrals, :780-839 ratios) and, as the adjoint check,
+ * src/diagnose's eta field (diagnose.f90:31-48, quick-tools1.f90:1-13).  Cylindrical geometry.
+ * ===================================================================================== */
+#define XEE_MAP_COLS 8 /* iters, r1, err, sum_Q, ke_gen, efficiency, sum_Qeta, efficiency_eta */
+
+typedef struct xee_map xee_map;
+typedef struct xee_map_desc {
+  int dtype;         /* XEE_F32 | XEE_F64 (working precision; inputs are float32 files)   */
+  int nr, nz;        /* grid points                                                       */
+  int nheat;         /* heating locations = independent solves per run                    */
+  int density_mode;  /* 0 DENSITY_NORMAL, 1 DENSITY_BOUSSINESQ (read-input.f90:33-40)      */
+  int arith, method; /* XEE_ARITH_*, XEE_METHOD_*                                         */
+  int device;        /* CUDA ordinal, -1 = current                                        */
+  int adjoint_check; /* 1: also solve L chi = -B once and report sum(Q eta)/sum(Q)        */
+  double Lr[2], Lz[2];  /* domain (read-input.f90:56)                                     */
+  double r1_rel_rms_f;  /* >0: per-location tolerance r1_n = r1_rel * rms(f_n)            */
+} xee_map_desc;
+
+/* A,B,C: HOST float32 nr x nz fields in the reference's .bin layout (field_tools.f90:30-52). */
+int xee_map_create(const xee_map_desc* desc, const float* A, const float* B, const float* C, xee_map** out);
+int xee_map_destroy(xee_map* m);
+/* heat: [nheat][5] doubles {r_c, z_c, sigma_r, sigma_z, Q0}; table: [nheat][XEE_MAP_COLS] doubles. */
+int xee_map_run_host(xee_map* m, const double* heat_host, const xee_solve_params* prm, double* table_host);
+int xee_map_run_dev(xee_map* m, const double* heat_dev, const xee_solve_params* prm, double* table_dev, void* stream);
+/* which: 0 psi [nheat][nz][nr], 1 f, 2 theta_B [(nz-1)][(nr-1)], 3 eta [nz][nr-1], 4 chi.  Plan dtype, HOST out. */
+int xee_map_get_field(xee_map* m, int which, void* host_out);
+int xee_map_sweep_kernel_stats(xee_map* m, double* ms_total, long long* launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

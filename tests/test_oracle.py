@@ -282,3 +282,18 @@ def test_energy_integrals_and_rhs_chain():
     exp = np.zeros((d.nz, d.nr)); exp[1:-1, 1:-1] = (dJ[1:, :] + dJ[:-1, :]) / 2 * k["g0"] / k["theta0"]
     assert np.allclose(rhs, exp, rtol=1e-10, atol=1e-30)
     assert np.all(rhs[0] == 0) and np.all(rhs[:, 0] == 0)
+
+
+def test_integral_check_identity_of_the_legacy_driver():
+    """old-diagnose/diagnose.f90:677-725: sum(Q eta) ~ (g0/theta0) sum(w theta) when A and B derive from one theta
+    field.  Validates the restated heating -> efficiency chain end to end on the oracle (first-order agreement)."""
+    from tests.map_oracle import efficiency_rows
+    from xlab_ee_fortran_b200 import workloads as W
+    nr, nz = 64, 48
+    Lr, Lz = (0.0, 6.0e5), (0.0, 1.5e4)
+    A, B, C = W.vortex_fields(nr, nz, Lr, Lz)
+    heat = W.heating_lattice(2, 2, Lr, Lz, 3 * Lr[1] / (nr - 1), 3 * Lz[1] / (nz - 1), r_frac=(0.02, 0.4), z_frac=(0.15, 0.75))
+    tab, *_ = efficiency_rows(A, B, C, Lr, Lz, heat, np.float64, dict(max_iter=400000, check_step=100, converge_time=2, r1_rel=1e-10))
+    assert np.all(tab[:, 2] == 0)
+    assert np.allclose(tab[:, 7], tab[:, 5], rtol=2e-2)
+    assert np.all(tab[:2, 5] > 1e-3)            # heating inside the vortex core is the efficient one

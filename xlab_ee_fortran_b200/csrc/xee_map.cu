@@ -1,0 +1,371 @@
+// xee_map.cu — the efficiency-map pipeline: one balanced vortex (A,B,C), many heating locations,
+// one elliptic solve per location, all on the device.
+//
+//   geometry (host scalars)     src/diagnose/initialize-variables.f90:45-67
+//   K1 build_abc_kernel         initialize-variables.f90:72-95
+//   K2 cal_coe_kernel           xtt-lib-fortran/elliptic_tools.f90:35-56
+//   background theta            src/old-diagnose/diagnose.f90:329-354, 503-509, 893-912 (testing_dt = 0)
+//   K7 heating_rhs_kernel       old-diagnose/diagnose.f90:383-387 (J = Q/(Cp Pi)), :396-406 (g/theta0 dJ/dr -> O)
+//   K3/K4 batched solve         elliptic_tools.f90:93-265
+//   K6 ke_generation_kernel     old-diagnose/diagnose.f90:915-941 (w), :1117-1127 (w theta), :1094-1113 (integral)
+//      sum_q_kernel             :1050-1071      qeta_kernel  :1073-1092 (adjoint check through eta)
+//
+// The legacy driver's latent bugs are not reproduced; the intended maths is:
+// Q is a genuine B-grid (nr-1,nz-1) field, theta is the background state (testing_dt = 0).
+#include "xee_plan.cuh"
+
+namespace xee {
+
+template <class T>
+struct PhysK {  // xtt-lib-fortran/constants.f90:4-5 evaluated in T
+  T g0 = T(9.8), theta0 = T(298.0), Rd = T(287.0), Cv, Cp, kappa, h0, p0 = T(101300.0);
+  PhysK() { Cv = T(5.0) / T(2.0) * Rd; Cp = Cv + Rd; kappa = Rd / Cp; h0 = Cp * theta0 / g0; }
+};
+
+// Heating blob n: Q(r,z) = Q0 exp(-((r-rc)/sr)^2 - ((z-zc)/sz)^2) sampled at B-cell centres.
+struct Heat { double rc, zc, sr, sz, q0; };
+
+template <class T>
+__device__ __forceinline__ T heat_q(const Heat& h, T r, T z) {
+  const double dr = ((double)r - h.rc) / h.sr, dz = ((double)z - h.zc) / h.sz;
+  return (T)(h.q0 * exp(-dr * dr - dz * dz));
+}
+
+// K7: f(i,j) = g0/theta0 * ( dJ(i,j) + dJ(i,j-1) )/2 on the O interior, 0 on the boundary,
+//     dJ(i,j) = (J(i,j)-J(i-1,j)) / ((ra(i+1)-ra(i-1))/2),  J(i,j) = Q(i,j)/(Cp*exner(j))   [B grid]
+template <class T>
+__global__ void heating_rhs_kernel(const Heat* __restrict__ heat, T* __restrict__ f, const T* __restrict__ ra,
+                                   const T* __restrict__ za, const T* __restrict__ ex, int nr, int nz, T g0, T theta0,
+                                   T Cp) {
+  using R = Rn<T>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0-based O index
+  const int j = blockIdx.y;
+  if (i >= nr) return;
+  const int n = blockIdx.z;
+  T out = T(0);
+  if (i > 0 && i < nr - 1 && j > 0 && j < nz - 1) {
+    const Heat h = heat[n];
+    // Fortran (I,J) = (i+1,j+1).  B cell (I,J) centre = ((ra(I)+ra(I+1))/2, (za(J)+za(J+1))/2)
+    const T rL = R::div(R::add(ra[i - 1], ra[i]), T(2)), rR = R::div(R::add(ra[i], ra[i + 1]), T(2));
+    const T zU = R::div(R::add(za[j], za[j + 1]), T(2)), zD = R::div(R::add(za[j - 1], za[j]), T(2));
+    const T dist = R::div(R::sub(ra[i + 1], ra[i - 1]), T(2));
+    const T cpU = R::mul(Cp, ex[j]), cpD = R::mul(Cp, ex[j - 1]);        // J(.,J) uses exner(J), J(.,J-1) exner(J-1)
+    const T dJU = R::div(R::sub(R::div(heat_q<T>(h, rR, zU), cpU), R::div(heat_q<T>(h, rL, zU), cpU)), dist);
+    const T dJD = R::div(R::sub(R::div(heat_q<T>(h, rR, zD), cpD), R::div(heat_q<T>(h, rL, zD), cpD)), dist);
+    out = R::div(R::mul(R::div(R::add(dJU, dJD), T(2)), g0), theta0);
+  }
+  f[(size_t)n * nr * nz + (size_t)j * nr + i] = out;
+}
+
+// Cell weight rho_ * rcuv * dr * dz of integrate_weight_B (old-diagnose/diagnose.f90:1038-1044), applied
+// left to right to `v` exactly as the reference multiplies.
+template <class T>
+__device__ __forceinline__ T weighted(T v, const T* ra, const T* rc, const T* za, const T* rho, int i, int j) {
+  using R = Rn<T>;
+  const T rcuv = R::div(R::add(rc[i], rc[i + 1]), T(2));
+  const T dr = R::sub(ra[i + 1], ra[i]);
+  const T dz = R::sub(za[j + 1], za[j]);
+  const T rho_ = R::div(R::add(rho[j + 1], rho[j]), T(2));
+  return R::mul(R::mul(R::mul(R::mul(v, rho_), rcuv), dr), dz);
+}
+
+// One block per heating location: sum_Q, (g0/theta0) * I[w theta], optional I[Q (eta(i,j)+eta(i,j+1))/2].
+// Deterministic tree reduction in double (the reference sums sequentially in real(4)).
+template <class T>
+__global__ void __launch_bounds__(256) map_integrals_kernel(const Heat* __restrict__ heat, const T* __restrict__ psi,
+                                                            const T* __restrict__ theta, const T* __restrict__ eta,
+                                                            const T* __restrict__ ra, const T* __restrict__ rc,
+                                                            const T* __restrict__ za, const T* __restrict__ rho,
+                                                            int nr, int nz, double* __restrict__ out /*[n][3]*/) {
+  using R = Rn<T>;
+  __shared__ double red[32];
+  const int n = blockIdx.x;
+  const Heat h = heat[n];
+  const T* p = psi + (size_t)n * nr * nz;
+  const int ncell = (nr - 1) * (nz - 1);
+  double sq = 0, swt = 0, sqe = 0;
+  for (int q = threadIdx.x; q < ncell; q += 256) {
+    const int i = q % (nr - 1), j = q / (nr - 1);
+    const T rm = R::div(R::add(ra[i], ra[i + 1]), T(2)), zm = R::div(R::add(za[j], za[j + 1]), T(2));
+    const T Q = heat_q<T>(h, rm, zm);
+    sq += (double)weighted<T>(Q, ra, rc, za, rho, i, j);
+    // w(i,j) = d_rcuvdr_O2A(rpsi)/rho(j)  (rpsiToUW, old-diagnose/diagnose.f90:921-927)
+    const T den_r = R::sub(ra[i + 1], ra[i]), rcm = R::div(R::add(rc[i], rc[i + 1]), T(2));
+    const T w0 = R::div(R::div(R::div(R::sub(p[(size_t)j * nr + i + 1], p[(size_t)j * nr + i]), den_r), rcm), rho[j]);
+    const T w1 = R::div(R::div(R::div(R::sub(p[(size_t)(j + 1) * nr + i + 1], p[(size_t)(j + 1) * nr + i]), den_r), rcm), rho[j + 1]);
+    const T wth = R::mul(R::div(R::add(w0, w1), T(2)), theta[(size_t)j * (nr - 1) + i]);        // cal_wtheta :1124
+    swt += (double)weighted<T>(wth, ra, rc, za, rho, i, j);
+    if (eta != nullptr) {
+      const T e = R::div(R::add(eta[(size_t)j * (nr - 1) + i], eta[(size_t)(j + 1) * (nr - 1) + i]), T(2));
+      sqe += (double)weighted<T>(R::mul(e, Q), ra, rc, za, rho, i, j);                         // cal_sum_Qeta :1088
+    }
+  }
+  const double a = block_sum(sq, red, threadIdx.x, 8);
+  const double b = block_sum(swt, red, threadIdx.x, 8);
+  const double c = block_sum(sqe, red, threadIdx.x, 8);
+  if (threadIdx.x == 0) { out[3 * n + 0] = a; out[3 * n + 1] = b; out[3 * n + 2] = c; }
+}
+
+// Background potential temperature on B from the basic state (testing_dt = 0):
+//   rhoA_A = (A(i,j)+A(i+1,j))/2, rhoB_B = 4-point average of B, rhoB_C(i,j) = (rhoB_B(i-1,j)+rhoB_B(i,j))/2 (i=2..nr-1)
+//   theta = relativeTheta(theta, rhoA_A*theta0/g0, rhoB_C*(-theta0/g0))          old-diagnose/diagnose.f90:893-912
+// One block; thread 0 integrates the bottom row in r, then one thread per column integrates in z.
+template <class T>
+__global__ void background_theta_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ theta,
+                                        const T* __restrict__ ra, const T* __restrict__ za, int nr, int nz, T g0,
+                                        T theta0) {
+  using R = Rn<T>;
+  const T k = R::div(theta0, g0);
+  auto rhoB_B = [&](int i, int j) {  // 0-based B cell
+    const size_t o = (size_t)j * nr + i;
+    return R::div(R::add(R::add(R::add(B[o], B[o + 1]), B[o + nr]), B[o + nr + 1]), T(4));
+  };
+  if (threadIdx.x == 0) {
+    theta[0] = theta0;
+    for (int i = 1; i < nr - 1; ++i) {   // Fortran i = 2..nr-1
+      const T dist = R::div(R::sub(ra[i + 1], ra[i - 1]), T(2));
+      const T rhoB_C = R::div(R::add(rhoB_B(i - 1, 0), rhoB_B(i, 0)), T(2));
+      theta[i] = R::add(theta[i - 1], R::mul(dist, R::mul(rhoB_C, -k)));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nr - 1; i += blockDim.x) {
+    for (int j = 1; j < nz - 1; ++j) {   // Fortran j = 2..nz-1
+      const T dist = R::div(R::sub(za[j + 1], za[j - 1]), T(2));
+      const T rhoA_A = R::div(R::add(A[(size_t)j * nr + i], A[(size_t)j * nr + i + 1]), T(2));
+      theta[(size_t)j * (nr - 1) + i] = R::add(theta[(size_t)(j - 1) * (nr - 1) + i], R::mul(dist, R::mul(rhoA_A, k)));
+    }
+  }
+}
+
+// f_basic = -(4-point average of rhoB_B) on the O interior   old-diagnose/diagnose.f90:524-530
+template <class T>
+__global__ void rhs_from_B_kernel(const T* __restrict__ B, T* __restrict__ f, int nr, int nz) {
+  using R = Rn<T>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= nr) return;
+  T out = T(0);
+  if (i > 0 && i < nr - 1 && j > 0 && j < nz - 1) {
+    auto bb = [&](int ii, int jj) {
+      const size_t o = (size_t)jj * nr + ii;
+      return R::div(R::add(R::add(R::add(B[o], B[o + 1]), B[o + nr]), B[o + nr + 1]), T(4));
+    };
+    out = -R::div(R::add(R::add(R::add(bb(i - 1, j - 1), bb(i - 1, j)), bb(i, j)), bb(i, j - 1)), T(4));
+  }
+  f[(size_t)j * nr + i] = out;
+}
+
+template <class T>
+__global__ void f32_to_T_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = (T)in[q];
+}
+template <class T>
+__global__ void rms_interior_kernel(const T* __restrict__ f, int nr, int nz, T scale, T* __restrict__ out) {
+  __shared__ double red[32];
+  const T* p = f + (size_t)blockIdx.x * nr * nz;
+  double s = 0;
+  for (int q = threadIdx.x; q < nr * nz; q += 256) {
+    const int i = q % nr, j = q / nr;
+    if (i > 0 && i < nr - 1 && j > 0 && j < nz - 1) s += (double)p[q] * (double)p[q];
+  }
+  const double t = block_sum(s, red, threadIdx.x, 8);
+  if (threadIdx.x == 0) out[blockIdx.x] = (T)(sqrt(t / ((double)(nr - 2) * (nz - 2))) * (double)scale);
+}
+
+struct MapBase {
+  xee_map_desc d{};
+  virtual ~MapBase() {}
+  virtual int run(const double* heat, bool heat_on_host, const xee_solve_params* prm, double* table, bool table_on_host,
+                  cudaStream_t s) = 0;
+  virtual PlanBase* plan() = 0;
+  virtual int get_field(int which, void* host_out) = 0;
+};
+
+template <class T>
+struct Map : MapBase {
+  Plan<T>* pl = nullptr;      // batched solves (shared operator)
+  Plan<T>* pl1 = nullptr;     // the single adjoint (chi) solve
+  T *A = nullptr, *B = nullptr, *C = nullptr, *ra = nullptr, *za = nullptr, *ex = nullptr, *rho = nullptr,
+    *theta = nullptr, *eta = nullptr, *chi = nullptr, *fchi = nullptr, *psi = nullptr, *f = nullptr, *r1v = nullptr;
+  Heat* heat_d = nullptr;
+  double* integ = nullptr;    // [n][3]
+  std::vector<T> h_ra, h_za, h_ex, h_rho;
+  T dr = 0, dz = 0;
+  size_t nn = 0;
+  PhysK<T> k;
+
+  PlanBase* plan() override { return pl; }
+
+  int init(const float* hA, const float* hB, const float* hC) {
+    const int nr = d.nr, nz = d.nz, nb = d.nheat;
+    nn = (size_t)nr * nz;
+    // geometry scalars on the host, in T, exactly as initialize-variables.f90:45-57 (std::pow == gfortran's **)
+    dr = (T(d.Lr[1]) - T(d.Lr[0])) / T(nr - 1);
+    dz = (T(d.Lz[1]) - T(d.Lz[0])) / T(nz - 1);
+    h_ra.resize(nr); h_za.resize(nz); h_ex.resize(nz); h_rho.resize(nz);
+    for (int i = 1; i <= nr; ++i) h_ra[i - 1] = T(d.Lr[0]) + T(i - 1) * dr;
+    for (int j = 1; j <= nz; ++j) {
+      h_za[j - 1] = T(d.Lz[0]) + T(j - 1) * dz;
+      h_ex[j - 1] = d.density_mode == 0 ? (T(1.0) - h_za[j - 1] / k.h0) : T(1.0);
+      h_rho[j - 1] = d.density_mode == 0 ? k.p0 / (k.theta0 * k.Rd) * std::pow(h_ex[j - 1], T(1.0) / k.kappa - T(1.0)) : T(1.0);
+    }
+    xee_plan_desc pd{};
+    pd.dtype = d.dtype; pd.nx = nr; pd.ny = nz; pd.nbatch = nb; pd.shared_coe = 1; pd.arith = d.arith; pd.method = d.method;
+    pd.device = d.device;
+    pl = new Plan<T>(); pl->d = pd;
+    if (pl->init()) return 1;
+    cudaStream_t s = pl->own_stream;
+    XEE_CHECK(cudaMalloc(&A, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&B, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&C, sizeof(T) * nn));
+    XEE_CHECK(cudaMalloc(&ra, sizeof(T) * nr)); XEE_CHECK(cudaMalloc(&za, sizeof(T) * nz));
+    XEE_CHECK(cudaMalloc(&ex, sizeof(T) * nz)); XEE_CHECK(cudaMalloc(&rho, sizeof(T) * nz));
+    XEE_CHECK(cudaMalloc(&theta, sizeof(T) * (nr - 1) * (nz - 1)));
+    XEE_CHECK(cudaMalloc(&psi, sizeof(T) * nn * nb)); XEE_CHECK(cudaMalloc(&f, sizeof(T) * nn * nb));
+    XEE_CHECK(cudaMalloc(&r1v, sizeof(T) * nb));
+    XEE_CHECK(cudaMalloc(&heat_d, sizeof(Heat) * nb)); XEE_CHECK(cudaMalloc(&integ, sizeof(double) * 3 * nb));
+    XEE_CHECK(cudaMemcpyAsync(ra, h_ra.data(), sizeof(T) * nr, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(za, h_za.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(ex, h_ex.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(rho, h_rho.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
+    // inputs arrive in the reference's file format: headerless float32, i fastest (field_tools.f90:30-52)
+    float* stage = nullptr;
+    XEE_CHECK(cudaMalloc(&stage, sizeof(float) * nn * 3));
+    XEE_CHECK(cudaMemcpyAsync(stage, hA, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(stage + nn, hB, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(stage + 2 * nn, hC, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
+    const unsigned gb = (unsigned)((nn + 255) / 256);
+    f32_to_T_kernel<T><<<gb, 256, 0, s>>>(stage, A, nn); XEE_LAUNCH_OK();
+    f32_to_T_kernel<T><<<gb, 256, 0, s>>>(stage + nn, B, nn); XEE_LAUNCH_OK();
+    f32_to_T_kernel<T><<<gb, 256, 0, s>>>(stage + 2 * nn, C, nn); XEE_LAUNCH_OK();
+    // K1 + K2 (cylindrical: rcuva = ra)
+    T *a = nullptr, *b = nullptr, *c = nullptr;
+    XEE_CHECK(cudaMalloc(&a, sizeof(T) * (nr - 1) * (nz - 2))); XEE_CHECK(cudaMalloc(&b, sizeof(T) * (nr - 1) * (nz - 1)));
+    XEE_CHECK(cudaMalloc(&c, sizeof(T) * (nr - 2) * (nz - 1)));
+    dim3 blk(64, 4), g((nr + 63) / 64, (nz + 3) / 4);
+    build_abc_kernel<T><<<g, blk, 0, s>>>(A, B, C, ra, rho, a, b, c, nr, nz); XEE_LAUNCH_OK();
+    XEE_CHECK(cudaStreamSynchronize(s));
+    if (pl->set_abc(a, b, c, (double)dr, (double)dz)) return 1;
+    background_theta_kernel<T><<<1, 256, 0, s>>>(A, B, theta, ra, za, nr, nz, k.g0, k.theta0); XEE_LAUNCH_OK();
+    if (d.adjoint_check) {
+      pd.nbatch = 1;
+      pl1 = new Plan<T>(); pl1->d = pd;
+      if (pl1->init()) return 1;
+      XEE_CHECK(cudaStreamSynchronize(s));
+      if (pl1->set_abc(a, b, c, (double)dr, (double)dz)) return 1;
+      XEE_CHECK(cudaMalloc(&eta, sizeof(T) * (nr - 1) * nz)); XEE_CHECK(cudaMalloc(&chi, sizeof(T) * nn));
+      XEE_CHECK(cudaMalloc(&fchi, sizeof(T) * nn));
+    }
+    XEE_CHECK(cudaStreamSynchronize(s));
+    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(stage);
+    return 0;
+  }
+  ~Map() override {
+    delete pl; delete pl1;
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ra); cudaFree(za); cudaFree(ex); cudaFree(rho); cudaFree(theta);
+    cudaFree(eta); cudaFree(chi); cudaFree(fchi); cudaFree(psi); cudaFree(f); cudaFree(r1v); cudaFree(heat_d); cudaFree(integ);
+  }
+
+  // table row: iters, r1, err, sum_Q, ke_gen=(g0/theta0) I[w theta], eff=ke_gen/sum_Q, sum_Qeta, eff_eta=sum_Qeta/sum_Q
+  int run(const double* heat, bool heat_on_host, const xee_solve_params* prm_in, double* table, bool table_on_host,
+          cudaStream_t s) override {
+    const int nr = d.nr, nz = d.nz, nb = d.nheat;
+    if (!s) s = pl->own_stream;
+    XEE_CHECK(cudaMemcpyAsync(heat_d, heat, sizeof(Heat) * nb, heat_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    dim3 gf((nr + 127) / 128, nz, nb);
+    heating_rhs_kernel<T><<<gf, 128, 0, s>>>(heat_d, f, ra, za, ex, nr, nz, k.g0, k.theta0, k.Cp); XEE_LAUNCH_OK();
+    XEE_CHECK(cudaMemsetAsync(psi, 0, sizeof(T) * nn * nb, s));     // rpsi = 0: boundary condition and first guess
+    xee_solve_params prm = *prm_in;
+    if (d.r1_rel_rms_f > 0) {   // tolerance relative to each location's own forcing: r1_n = r1_rel * rms(f_n)
+      rms_interior_kernel<T><<<nb, 256, 0, s>>>(f, nr, nz, (T)d.r1_rel_rms_f, r1v); XEE_LAUNCH_OK();
+      prm.r1 = 1.0; prm.r1_per_solve = r1v;
+    }
+    std::vector<int> iters(nb), err(nb);
+    std::vector<double> r1o(nb), r2o(nb);
+    if (pl->solve(psi, f, &prm, iters.data(), r1o.data(), r2o.data(), err.data(), s, false, nullptr, 0)) return 1;
+    if (d.adjoint_check) {
+      dim3 g1((nr + 127) / 128, nz, 1);
+      rhs_from_B_kernel<T><<<g1, 128, 0, s>>>(B, fchi, nr, nz); XEE_LAUNCH_OK();
+      XEE_CHECK(cudaMemsetAsync(chi, 0, sizeof(T) * nn, s));
+      xee_solve_params p1 = *prm_in;
+      T* r1c = nullptr;
+      if (d.r1_rel_rms_f > 0) {
+        XEE_CHECK(cudaMalloc(&r1c, sizeof(T)));
+        rms_interior_kernel<T><<<1, 256, 0, s>>>(fchi, nr, nz, (T)d.r1_rel_rms_f, r1c); XEE_LAUNCH_OK();
+        p1.r1 = 1.0; p1.r1_per_solve = r1c;
+      }
+      int it1, e1; double a1, a2;
+      const int rc = pl1->solve(chi, fchi, &p1, &it1, &a1, &a2, &e1, s, false, nullptr, 0);
+      if (r1c) cudaFree(r1c);
+      if (rc) return 1;
+      dim3 ge((nr - 1 + 127) / 128, nz, 1);
+      eta_kernel<T><<<ge, 128, 0, s>>>(chi, eta, ra, ra, rho, ex, nr, nz, k.g0, k.Cp, k.theta0); XEE_LAUNCH_OK();
+    }
+    map_integrals_kernel<T><<<nb, 256, 0, s>>>(heat_d, psi, theta, d.adjoint_check ? eta : nullptr, ra, ra, za, rho, nr, nz, integ);
+    XEE_LAUNCH_OK();
+    std::vector<double> hi(3 * (size_t)nb);
+    XEE_CHECK(cudaMemcpyAsync(hi.data(), integ, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, s));
+    XEE_CHECK(cudaStreamSynchronize(s));
+    std::vector<double> rows((size_t)nb * XEE_MAP_COLS);
+    const double gth = (double)k.g0 / (double)k.theta0;
+    for (int n = 0; n < nb; ++n) {
+      double* r = &rows[(size_t)n * XEE_MAP_COLS];
+      r[0] = iters[n]; r[1] = r1o[n]; r[2] = err[n];
+      r[3] = hi[3 * n]; r[4] = hi[3 * n + 1] * gth; r[5] = r[4] / r[3];
+      r[6] = hi[3 * n + 2]; r[7] = r[6] / r[3];
+    }
+    if (table_on_host) memcpy(table, rows.data(), sizeof(double) * rows.size());
+    else XEE_CHECK(cudaMemcpy(table, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  int get_field(int which, void* out) override {
+    const int nr = d.nr, nz = d.nz;
+    const void* src = nullptr; size_t bytes = 0;
+    switch (which) {
+      case 0: src = psi; bytes = sizeof(T) * nn * d.nheat; break;
+      case 1: src = f; bytes = sizeof(T) * nn * d.nheat; break;
+      case 2: src = theta; bytes = sizeof(T) * (nr - 1) * (nz - 1); break;
+      case 3: src = eta; bytes = sizeof(T) * (nr - 1) * nz; break;
+      case 4: src = chi; bytes = sizeof(T) * nn; break;
+      default: return fail("xee_map_get_field: unknown field");
+    }
+    if (!src) return fail("xee_map_get_field: field not computed (adjoint_check off?)");
+    XEE_CHECK(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+};
+
+}  // namespace xee
+
+using namespace xee;
+struct xee_map { MapBase* impl; };
+
+extern "C" {
+int xee_map_create(const xee_map_desc* desc, const float* A, const float* B, const float* C, xee_map** out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("xee: no CUDA device available - this library has no CPU fallback");
+  if (desc->device >= 0) XEE_CHECK(cudaSetDevice(desc->device));
+  if (desc->nr < 4 || desc->nz < 4 || desc->nheat < 1) return fail("xee_map: nr, nz >= 4 and nheat >= 1 required");
+  MapBase* m = nullptr; int rc;
+  if (desc->dtype == XEE_F32) { auto* q = new Map<float>(); q->d = *desc; rc = q->init(A, B, C); m = q; }
+  else if (desc->dtype == XEE_F64) { auto* q = new Map<double>(); q->d = *desc; rc = q->init(A, B, C); m = q; }
+  else return fail("xee_map: dtype must be XEE_F32 or XEE_F64");
+  if (rc) { delete m; return 1; }
+  *out = new xee_map{m};
+  return 0;
+}
+int xee_map_destroy(xee_map* m) { if (m) { delete m->impl; delete m; } return 0; }
+int xee_map_run_host(xee_map* m, const double* heat, const xee_solve_params* prm, double* table) {
+  return m->impl->run(heat, true, prm, table, true, nullptr);
+}
+int xee_map_run_dev(xee_map* m, const double* heat_dev, const xee_solve_params* prm, double* table_dev, void* stream) {
+  return m->impl->run(heat_dev, false, prm, table_dev, false, (cudaStream_t)stream);
+}
+int xee_map_get_field(xee_map* m, int which, void* host_out) { return m->impl->get_field(which, host_out); }
+int xee_map_sweep_kernel_stats(xee_map* m, double* ms, long long* launches, int reset) {
+  PlanBase* p = m->impl->plan();
+  if (ms) *ms = p->sweep_ms;
+  if (launches) *launches = p->sweep_launches;
+  if (reset) { p->sweep_ms = 0; p->sweep_launches = 0; }
+  return 0;
+}
+}  // extern "C"
