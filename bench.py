@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native elliptic-solve hot path.
+
+Metric (BASELINE.json): elliptic solves/sec and GB/s vs HBM peak on the 512x256 r-z grid.
+Workload: one shard of the efficiency map (BASELINE config 4): `--nheat` heating locations per GPU
+(default 512; 8 GPUs = 4096 locations) on a 512x256 grid, fp64, one balanced vortex shared by all
+solves, every solve iterated to r1 = 1e-12 * rms(f_n).  A "step" is one complete pass: heating RHS
+built on the device, all solves to tolerance, energy integrals, efficiency table (+ the gather at N>1).
+
+  python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host cores
+
+`value`  : whole-job solves/s with the operator and heating parameters resident in HBM.
+`e2e`    : the same metric through the host-facing call (HOST A,B,C + heating table in, efficiency
+           table out; H2D/D2H and operator assembly inside the timed region).
+`roofline`: dominant kernel = the sweep kernel; achieved = algorithmic bytes / CUDA-event time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NR, NZ = 512, 256
+LR, LZ = (0.0, 1.0e6), (0.0, 1.5e4)
+R1_REL = 1e-12
+CONSTANTS = os.path.join(ROOT, "profiles", "workload_constants.json")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_constants():
+    return json.load(open(CONSTANTS)) if os.path.exists(CONSTANTS) else {}
+
+
+def heat_rows(total):
+    from xlab_ee_fortran_b200 import workloads as W
+    dr, dz = LR[1] / (NR - 1), LZ[1] / (NZ - 1)
+    n_r = 64
+    assert total % n_r == 0, "total heating locations must be a multiple of 64"
+    return W.heating_lattice(n_r, total // n_r, LR, LZ, 2 * dr, 2 * dz)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample(sweeps, threads, method_sweeps):
+    """The reference algorithm (oracle literal restatement: 4 passes per sweep, reference loop order) on the host
+    cores: `threads` independent 512x256 fp64 solves of this workload, `sweeps` Jacobi sweeps each, one per thread.
+    solves/s is extrapolated linearly to `method_sweeps` (the Jacobi sweep count to the bench tolerance)."""
+    from oracle import oracle as O
+    from xlab_ee_fortran_b200 import workloads as W
+    from tests.map_oracle import heat_field
+    dt = np.float64
+    A, B, C = W.vortex_fields(NR, NZ, LR, LZ)
+    d = O.Domain(LR, LZ, NR, NZ, 0, 0)
+    g = O.geometry(d, dt)
+    a, b, c = O.build_abc(A.astype(dt), B.astype(dt), C.astype(dt), d)
+    coe, _ = O.cal_coe(a, b, c, g["dr"], g["dz"], NR, NZ)
+    rows = heat_rows(max(64, ((threads + 63) // 64) * 64))[:threads]
+    F = np.stack([O.rhs_thermal(heat_field(r, g, dt), d)[1] for r in rows])
+    P = np.zeros_like(F)
+    res = O.solve_batch(sweeps, 100, 10, 5, 1e-300, 0.0, 1.0, P, coe, F, threads=threads)
+    sec = res["seconds"]
+    sweeps_per_s = threads * sweeps / sec                 # aggregate over the cores
+    return dict(seconds=sec, sweeps_per_s=sweeps_per_s, solves_per_s=sweeps_per_s / method_sweeps,
+                point_sweeps_per_s=sweeps_per_s * (NR - 2) * (NZ - 2))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    k = workload_constants()
+    js = float(k.get("jacobi_sweeps_to_tol", 0)) or None
+    cores = O.max_threads()
+    vals = []
+    sweeps = args.ref_sweeps
+    for s in range(args.warmup + args.steps):
+        r = cpu_sample(sweeps, cores, js or 1.0)
+        if s >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["solves_per_s"] for r in vals])) if js else None
+    ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
+    sample = (f"{cores} independent 512x256 fp64 solves (one per host thread), {sweeps} reference Jacobi sweeps each per step; "
+              f"solves/s extrapolated linearly to the {js:.0f} sweeps Jacobi needs for r1=1e-12*rms(f) on this workload "
+              f"(measured with the bit-identical GPU Jacobi path, profiles/workload_constants.json)" if js else "no sweep-count constant")
+    line = {"impl": "reference", "metric": "elliptic_solves_per_sec", "value": v, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, "jacobi (reference algorithm, elliptic_tools.f90:93-265)"),
+            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
+                             "point_sweeps_per_s": float(np.mean([r["point_sweeps_per_s"] for r in vals]))},
+            "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, method):
+    return {"workload": f"efficiency-map shard (BASELINE config 4): {args.nheat} heating locations per GPU on a {NR}x{NZ} r-z grid, "
+                        f"shared vortex operator, every solve to r1=1e-12*rms(f)",
+            "grid": [NR, NZ], "nheat_per_gpu": args.nheat, "method": method, "tolerance": "r1 = 1e-12 * rms(f_n), r2 off",
+            "l2_policy": "inputs larger than L2 (psi+psi'+f = %.2f GiB per GPU vs 126 MB L2)" % (3 * args.nheat * NR * NZ * 8 / 2 ** 30)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200 import plan as P
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.efficiency_map import EfficiencyMap, gather_rows, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    total = args.nheat * world
+    rows = heat_rows(total)
+    a, b = partition(total, world, rank)
+    my = np.ascontiguousarray(rows[a:b]); nloc = b - a
+    A, B, C = W.vortex_fields(NR, NZ, LR, LZ)
+    prm = X.SolveParams(max_iter=args.max_iter, check_step=100, converge_time=2, r1=1.0, r2=0.0, alpha=1.0, sync_every=2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ value leg (inputs resident in HBM)
+    m = EfficiencyMap(A, B, C, LR, LZ, nloc, "f64", arith=args.arith, method=args.method, r1_rel=R1_REL, device=local)
+    heat_t = torch.from_numpy(my).cuda(); table_t = torch.zeros((nloc, 8), dtype=torch.float64, device="cuda")
+
+    def step():
+        m.run_dev(heat_t, table_t, prm)
+        return gather_rows(table_t, total) if world > 1 else table_t
+
+    for _ in range(args.warmup):
+        out = step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler: sampler.start()
+    barrier()
+    m.sweep_kernel_stats(reset=True); P.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = P.launch_count()
+    sweep_ms, sweep_launches = m.sweep_kernel_stats()
+    tab = table_t.cpu().numpy()
+    clocks = sampler.finish() if sampler else None
+    ms_per_step = ms_total / args.steps
+    value = total / (ms_per_step * 1e-3)
+    assert np.all(tab[:, 2] == 0), "a solve hit max_iter: not converged"
+    # roofline of the dominant kernel: useful point-sweeps actually performed (per-solve sweep counts) x bytes
+    interior = (NR - 2) * (NZ - 2)
+    fields = 4 if args.method == "chebyshev" else 3           # psi read, psi write, f read (+ psi_{k-1} for Chebyshev)
+    b_alg = 8.0 * (fields + 9.0 / nloc)
+    alg_bytes = float(tab[:, 0].sum()) * interior * b_alg * args.steps
+    achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    k = workload_constants()
+    traffic = k.get("sweep_kernel_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "sweep (K3/K4)",
+                "avg_launch_us": sweep_ms / max(sweep_launches, 1) * 1e3, "launches": sweep_launches,
+                "algorithmic_bytes_per_point_sweep": b_alg, "kernel_share_of_step": sweep_ms / ms_total,
+                "sweeps_per_solve": [float(tab[:, 0].min()), float(tab[:, 0].max())]}
+    m.close(); del heat_t, table_t
+    # ------------------------------------------------------------------ e2e leg (host buffers, whole call)
+    import ctypes
+    hA, hB, hC = (torch.from_numpy(x).pin_memory() for x in (A, B, C))
+    hheat = torch.from_numpy(my).pin_memory()
+
+    def e2e_step():
+        mm = EfficiencyMap(hA.numpy(), hB.numpy(), hC.numpy(), LR, LZ, nloc, "f64", arith=args.arith, method=args.method,
+                           r1_rel=R1_REL, device=local)
+        t = mm.run(hheat.numpy(), prm)
+        mm.close()
+        if world > 1:
+            return gather_rows(torch.from_numpy(t).cuda(), total)
+        return t
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        out2 = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.e2e_steps
+    e2e = {"value": total / (e2e_ms * 1e-3), "unit": "solves/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(3 * NR * NZ * 4 + nloc * 40), "d2h_bytes_per_step": int(nloc * (8 * 8 + 4 + 4 + 8 + 8)),
+           "call": "EfficiencyMap(A,B,C host float32).run(heat host) -> table host (xee_map_create + xee_map_run_host + xee_map_destroy)"}
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        js = float(k.get("jacobi_sweeps_to_tol", 0)) or None
+        cores = O.max_threads()
+        r = cpu_sample(args.ref_sweeps, cores, js or 1.0)
+        cpu = {"value": r["solves_per_s"] if js else None, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} solves x {args.ref_sweeps} reference Jacobi sweeps (512x256 fp64, one solve per thread, {r['seconds']:.1f} s); "
+                         f"extrapolated to {js:.0f} sweeps/solve (Jacobi to the bench tolerance)" if js else "n/a",
+               "point_sweeps_per_s": r["point_sweeps_per_s"]}
+    if rank == 0:
+        line = {"metric": "elliptic_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, f"{args.method} ({args.arith} arithmetic)"),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "efficiency_range": [float(tab[:, 5].min()), float(tab[:, 5].max())]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nheat", type=int, default=512, help="heating locations (independent solves) per GPU")
+    ap.add_argument("--method", default="chebyshev", choices=["chebyshev", "jacobi"])
+    ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--max-iter", type=int, default=2000000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-sweeps", type=int, default=8000, help="Jacobi sweeps per solve in one CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,7 +47,7 @@ class EfficiencyMap:
         _lib.check(_lib.lib().xee_map_create(C.byref(d), p(A), p(B), p(Cf), C.byref(self._h)), "map_create")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().xee_map_destroy(self._h)
             self._h = None
 

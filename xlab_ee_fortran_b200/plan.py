@@ -69,7 +69,7 @@ class Plan:
             _lib.check(L.xee_plan_create(C.byref(d), C.byref(self._h)), "plan_create")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().xee_plan_destroy(self._h)
             self._h = None
 
