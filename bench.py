@@ -239,16 +239,18 @@ def run_ours(args):
             return gather_rows(torch.from_numpy(t).cuda(), total)
         return t
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        out2 = e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.e2e_steps
-    e2e = {"value": total / (e2e_ms * 1e-3), "unit": "solves/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(3 * NR * NZ * 4 + nloc * 40), "d2h_bytes_per_step": int(nloc * (8 * 8 + 4 + 4 + 8 + 8)),
-           "call": "EfficiencyMap(A,B,C host float32).run(heat host) -> table host (xee_map_create + xee_map_run_host + xee_map_destroy)"}
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out2 = e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.e2e_steps
+        e2e = {"value": total / (e2e_ms * 1e-3), "unit": "solves/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(3 * NR * NZ * 4 + nloc * 40), "d2h_bytes_per_step": int(nloc * (8 * 8 + 4 + 4 + 8 + 8)),
+               "call": "EfficiencyMap(A,B,C host float32).run(heat host) -> table host (xee_map_create + xee_map_run_host + xee_map_destroy)"}
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
