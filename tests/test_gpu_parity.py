@@ -245,3 +245,38 @@ def test_debug_prints_match_reference_format(capfd):
     assert " ----- Solve Elliptic Inputs -----" in out
     assert out.count("Iter: ") == 3 and "Iter:       10, err_now: " in out
     assert " Elliptic Tools: [Error] Max iteration reached." in out
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shape,nb", [((140, 70), 20), ((512, 256), 5), ((260, 13), 37), ((8, 4), 3)])
+def test_tma_kernel_matches_direct_kernel_and_oracle_bitwise(name, shape, nb):
+    """v2 (TMA pipeline, kernel=2) against v1 (direct, kernel=1) and the oracle: STRICT iterates bit-identical,
+    partial tiles on every edge, more solves than one work-unit chunk, residual partials per TMA tile."""
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = shape
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=nx + nb)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    F = np.stack([f * dt(k + 1) for k in range(nb)]); P = np.stack([x0 * dt(1 + 0.25 * k) for k in range(nb)])
+    res = {}
+    for kern in (1, 2):
+        plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=True, arith="strict", kernel=kern)
+        plan.set_coe_aos(coe)
+        psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+        out = plan.solve(psi, ft, X.SolveParams(max_iter=57, check_step=10, converge_time=10, r1=1e-30, r2=1.0, alpha=0.9))
+        res[kern] = (psi.cpu().numpy(), out)
+        plan.close()
+    assert np.array_equal(res[1][0], res[2][0])
+    assert np.allclose(res[1][1]["r1"], res[2][1]["r1"], rtol=1e-12)
+    rb = O.solve_batch(57, 10, 10, 5, 1e-30, 1.0, 0.9, P, coe, F, threads=4)
+    assert np.array_equal(res[2][0], rb["dat"]) and list(res[2][1]["iters"]) == list(rb["max_iter"])
+    assert np.allclose(res[2][1]["r1"], rb["r1"], rtol=RES_TOL[name])
+    # FAST + Chebyshev: the two kernels run the same FMA sequence -> identical bits as well
+    for kern in (1, 2):
+        plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=True, arith="fast", method="chebyshev", kernel=kern)
+        plan.set_coe_aos(coe)
+        psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+        prm = X.SolveParams(max_iter=2000, check_step=10, converge_time=2, r1=1e-3 if name == "f64" else 1e-1, r2=0.0, rho_jacobi=0.97)
+        out = plan.solve(psi, ft, prm)
+        res[kern] = (psi.cpu().numpy(), out)
+        plan.close()
+    assert np.array_equal(res[1][0], res[2][0]) and list(res[1][1]["iters"]) == list(res[2][1]["iters"])

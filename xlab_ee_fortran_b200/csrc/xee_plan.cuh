@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "xee_kernels.cuh"
+#include "xee_sweep_tma.cuh"
 
 namespace xee {
 
@@ -72,6 +73,11 @@ struct Plan : PlanBase {
   size_t ev_used = 0;
   cudaEvent_t poll_ev[4]{};
   double cheb_rho = 0.0;
+  // v2 (TMA) sweep kernel: launch geometry + tensor maps of the buffers of the current call
+  bool use_tma = false;
+  int tma_tiles_x = 0, tma_tiles_y = 0, tma_chunk = 1, tma_nchunks = 1, tma_grid = 1, tma_nstage = 6, num_sms = 148;
+  CUtensorMap map_halo[2]{}, map_plain[2]{}, map_f{};
+  const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
 
   int init() {
     nn = (size_t)d.nx * d.ny;
@@ -104,6 +110,72 @@ struct Plan : PlanBase {
     }
     gz = (d.nbatch + spb - 1) / spb;
     XEE_CHECK(cudaMalloc(&partial, sizeof(double) * (size_t)ntiles * nb));
+    int dev = 0;
+    XEE_CHECK(cudaGetDevice(&dev));
+    XEE_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // Kernel variant: 1 = v1 direct, 2 = v2 TMA pipeline.  auto: TMA for shared-operator batches whose rows are
+    // 16-byte multiples (TMA global-stride rule); everything else takes the direct kernel.
+    int want = d.kernel > 0 ? d.kernel : env_int("XEE_KERNEL", 0);
+    const bool tma_ok = d.shared_coe && ((size_t)d.nx * sizeof(T)) % 16 == 0 && d.nx >= 8 && d.ny >= 4;
+    if (want == 2 && !tma_ok) return fail("xee: kernel=2 (TMA) needs a shared operator and nx*sizeof(real) % 16 == 0");
+    use_tma = (want == 2) || (want == 0 && tma_ok && (long long)d.nbatch * d.nx * d.ny >= (1 << 16));
+    if (use_tma) {
+      tma_tiles_x = (d.nx - 2 + tma::TW - 1) / tma::TW;
+      tma_tiles_y = (d.ny - 2 + tma::TH - 1) / tma::TH;
+      const int nt = tma_tiles_x * tma_tiles_y;
+      // chunk = solves per work unit (operator registers reused across them).  Pick the chunk in [4,32] that
+      // minimises the makespan of the static round-robin over the persistent CTAs.
+      const int grid_cap = num_sms;
+      long long best = -1; tma_chunk = 1;
+      for (int ch = std::min(32, d.nbatch); ch >= std::min(4, d.nbatch); --ch) {
+        const int nch = (d.nbatch + ch - 1) / ch;
+        const long long units = (long long)nt * nch;
+        const int g = (int)std::min<long long>(grid_cap, units);
+        const long long makespan = ((units + g - 1) / g) * ch + 2;   // +2: operator reload per unit
+        if (best < 0 || makespan < best) { best = makespan; tma_chunk = ch; }
+      }
+      tma_nchunks = (d.nbatch + tma_chunk - 1) / tma_chunk;
+      tma_grid = (int)std::min<long long>(grid_cap, (long long)nt * tma_nchunks);
+      tma_nstage = std::max(2, std::min(env_int("XEE_TMA_STAGES", 6), tma::NSTAGE_MAX));
+      if (nt > ntiles) return fail("xee: internal: partial buffer too small for the TMA tiling");
+    }
+    return 0;
+  }
+  int sweep_ntiles() const { return use_tma ? tma_tiles_x * tma_tiles_y : ntiles; }
+
+  // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).
+  static int encode_map(CUtensorMap* m, const void* base, int nx, int ny, int nb, int box_w, int box_h) {
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Fn fn = nullptr;
+    if (!fn) {
+      void* p = nullptr; cudaDriverEntryPointQueryResult q;
+      XEE_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+      if (!p) return fail("xee: cuTensorMapEncodeTiled not available from the driver");
+      fn = (Fn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nb};
+    const cuuint64_t strides[2] = {(cuuint64_t)nx * sizeof(T), (cuuint64_t)nx * ny * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = fn(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "xee: cuTensorMapEncodeTiled failed (%d)", (int)r); return fail(b); }
+    return 0;
+  }
+  // (Re)build the tensor maps when the buffers of this call differ from the cached ones.
+  int prepare_maps(const T* x0, const T* x1buf, const T* f, int nb) {
+    if (!use_tma) return 0;
+    if (map_ptrs[0] == x0 && map_ptrs[1] == x1buf && map_ptrs[2] == f) return 0;
+    if (((uintptr_t)x0 | (uintptr_t)x1buf | (uintptr_t)f) & 15) return fail("xee: TMA path needs 16-byte aligned field buffers");
+    const int hw = tma::Cfg<T>::HALO_W;
+    if (encode_map(&map_halo[0], x0, d.nx, d.ny, nb, hw, tma::TH + 2) || encode_map(&map_halo[1], x1buf, d.nx, d.ny, nb, hw, tma::TH + 2) ||
+        encode_map(&map_plain[0], x0, d.nx, d.ny, nb, hw, tma::TH) || encode_map(&map_plain[1], x1buf, d.nx, d.ny, nb, hw, tma::TH) ||
+        encode_map(&map_f, f, d.nx, d.ny, nb, hw, tma::TH))
+      return 1;
+    map_ptrs[0] = x0; map_ptrs[1] = x1buf; map_ptrs[2] = f;
     return 0;
   }
   ~Plan() override {
@@ -170,7 +242,7 @@ struct Plan : PlanBase {
     a.coe_set_stride = d.shared_coe ? 0 : (long long)kPlanes * nn;
     a.field_stride = (long long)nn;
     a.nx = d.nx; a.ny = d.ny; a.nbatch = d.nbatch; a.spb = spb;
-    a.alpha = alpha; a.omega = omega; a.done = done; a.partial = partial; a.ntiles = ntiles;
+    a.alpha = alpha; a.omega = omega; a.done = done; a.partial = partial; a.ntiles = sweep_ntiles();
     return a;
   }
 
@@ -180,7 +252,39 @@ struct Plan : PlanBase {
     if (check) sweep_direct_kernel<T, ARITH, MODE, true><<<g, blk, 0, s>>>(a);
     else sweep_direct_kernel<T, ARITH, MODE, false><<<g, blk, 0, s>>>(a);
   }
+  template <int ARITH, int MODE, bool CHECK>
+  int launch_tma_inst(const TmaSweepArgs<T>& P, const CUtensorMap& ms, const CUtensorMap& mp, cudaStream_t s) {
+    constexpr int stage = tma::Cfg<T>::PSI_BYTES + tma::Cfg<T>::FLD_BYTES + (MODE == MODE_CHEBYSHEV ? tma::Cfg<T>::FLD_BYTES : 0);
+    const size_t smem = (size_t)stage * P.nstage;
+    static bool attr_done = false;
+    if (!attr_done) {
+      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_done = true;
+    }
+    sweep_tma_kernel<T, ARITH, MODE, CHECK><<<tma_grid, tma::NTHREADS, smem, s>>>(P, ms, mp, map_f);
+    return 0;
+  }
+  template <int ARITH, int MODE>
+  int launch_tma_mode(const TmaSweepArgs<T>& P, const CUtensorMap& ms, const CUtensorMap& mp, bool check, cudaStream_t s) {
+    return check ? launch_tma_inst<ARITH, MODE, true>(P, ms, mp, s) : launch_tma_inst<ARITH, MODE, false>(P, ms, mp, s);
+  }
+  int launch_sweep_tma(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
+    TmaSweepArgs<T> P{};
+    P.a = a; P.tiles_x = tma_tiles_x; P.tiles_y = tma_tiles_y; P.nchunks = tma_nchunks; P.chunk = tma_chunk; P.nstage = tma_nstage;
+    const int si = (a.src == (const T*)map_ptrs[0]) ? 0 : 1;      // which ping-pong buffer is the source
+    const CUtensorMap& ms = map_halo[si];
+    const CUtensorMap& mp = map_plain[si ^ 1];
+    const bool strict = d.arith == XEE_ARITH_STRICT;
+    int rc;
+    if (mode == MODE_JACOBI) rc = strict ? launch_tma_mode<XEE_ARITH_STRICT, MODE_JACOBI>(P, ms, mp, check, s) : launch_tma_mode<XEE_ARITH_FAST, MODE_JACOBI>(P, ms, mp, check, s);
+    else rc = strict ? launch_tma_mode<XEE_ARITH_STRICT, MODE_CHEBYSHEV>(P, ms, mp, check, s) : launch_tma_mode<XEE_ARITH_FAST, MODE_CHEBYSHEV>(P, ms, mp, check, s);
+    if (rc) return rc;
+    XEE_LAUNCH_OK();
+    return 0;
+  }
   int launch_sweep(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
+    if (use_tma && mode != MODE_APPLY && a.nbatch == d.nbatch && (a.src == map_ptrs[0] || a.src == map_ptrs[1]))
+      return launch_sweep_tma(a, mode, check, s);
     const bool strict = d.arith == XEE_ARITH_STRICT;
     if (mode == MODE_JACOBI) strict ? launch_mode<XEE_ARITH_STRICT, MODE_JACOBI>(a, check, s) : launch_mode<XEE_ARITH_FAST, MODE_JACOBI>(a, check, s);
     else if (mode == MODE_CHEBYSHEV) strict ? launch_mode<XEE_ARITH_STRICT, MODE_CHEBYSHEV>(a, check, s) : launch_mode<XEE_ARITH_FAST, MODE_CHEBYSHEV>(a, check, s);
@@ -226,6 +330,7 @@ struct Plan : PlanBase {
   int sweeps(void* psi, const void* f, double alpha, int nsw, double* rms, cudaStream_t s) override {
     T* x0 = (T*)psi;
     XEE_CHECK(cudaMemcpyAsync(x1, x0, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
+    if (prepare_maps(x0, x1, (const T*)f, d.nbatch)) return 1;
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
     const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
@@ -242,12 +347,13 @@ struct Plan : PlanBase {
     XEE_CHECK(cudaStreamSynchronize(s));
     harvest_events();
     if (rms && nsw > 0) {
-      std::vector<double> h((size_t)ntiles * d.nbatch);
+      const int nt = sweep_ntiles();
+      std::vector<double> h((size_t)nt * d.nbatch);
       XEE_CHECK(cudaMemcpy(h.data(), partial, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
       const double N = (double)(d.nx - 2) * (d.ny - 2);
       for (int n = 0; n < d.nbatch; ++n) {
         double t = 0;
-        for (int q = 0; q < ntiles; ++q) t += h[(size_t)n * ntiles + q];
+        for (int q = 0; q < nt; ++q) t += h[(size_t)n * nt + q];
         rms[n] = std::sqrt(t / N);
       }
     }
@@ -330,6 +436,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   XEE_LAUNCH_OK();
   // workspace = dat: both ping-pong buffers start as boundary + first guess (:166-171)
   XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+  if (prepare_maps(x0, x1, fd, nb)) return 1;
   const int ninterior = (d.nx - 2) * (d.ny - 2);
   const int lookahead = prm->sync_every > 0 ? prm->sync_every : 1;
   int cnt = 0, check_idx = 0, printed = 0;
@@ -352,7 +459,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     sweep_launches += chunk;
     XEE_CHECK(cudaEventRecord(e1, s));
     if ((cnt % check_step) == 0) {
-      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, ntiles, ninterior, cnt, check_idx, converge_time,
+      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
                                                   lost_rate, max_iter, prm->detect_explode);
       XEE_LAUNCH_OK();
       const int slot = check_idx & 3;
