@@ -198,6 +198,7 @@ struct Map : MapBase {
   PlanBase* plan() override { return pl; }
 
   int init(const float* hA, const float* hB, const float* hC) {
+    TraceTimer tt("map init (total)");
     const int nr = d.nr, nz = d.nz, nb = d.nheat;
     nn = (size_t)nr * nz;
     // geometry scalars on the host, in T, exactly as initialize-variables.f90:45-57 (std::pow == gfortran's **)
@@ -260,6 +261,7 @@ struct Map : MapBase {
     return 0;
   }
   ~Map() override {
+    TraceTimer tt("map destroy");
     delete pl; delete pl1;
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ra); cudaFree(za); cudaFree(ex); cudaFree(rho); cudaFree(theta);
     cudaFree(eta); cudaFree(chi); cudaFree(fchi); cudaFree(psi); cudaFree(f); cudaFree(r1v); cudaFree(heat_d); cudaFree(integ);
@@ -268,6 +270,7 @@ struct Map : MapBase {
   // table row: iters, r1, err, sum_Q, ke_gen=(g0/theta0) I[w theta], eff=ke_gen/sum_Q, sum_Qeta, eff_eta=sum_Qeta/sum_Q
   int run(const double* heat, bool heat_on_host, const xee_solve_params* prm_in, double* table, bool table_on_host,
           cudaStream_t s) override {
+    TraceTimer tt("map run (total)");
     const int nr = d.nr, nz = d.nz, nb = d.nheat;
     if (!s) s = pl->own_stream;
     XEE_CHECK(cudaMemcpyAsync(heat_d, heat, sizeof(Heat) * nb, heat_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));

@@ -4,6 +4,7 @@
 #pragma once
 #include <atomic>
 #include <cmath>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -41,6 +42,14 @@ inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+
+// XEE_TRACE=1: wall-clock phase timings on stderr (host side, after a device sync).
+struct TraceTimer {
+  const char* what; double t0; bool on;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  explicit TraceTimer(const char* w) : what(w), t0(0), on(env_int("XEE_TRACE", 0) != 0) { if (on) { cudaDeviceSynchronize(); t0 = now(); } }
+  ~TraceTimer() { if (on) { cudaDeviceSynchronize(); fprintf(stderr, "xee trace: %-28s %9.3f ms\n", what, (now() - t0) * 1e3); } }
+};
 
 struct PlanBase {
   xee_plan_desc d{};
@@ -80,6 +89,7 @@ struct Plan : PlanBase {
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
 
   int init() {
+    TraceTimer tt("plan init");
     nn = (size_t)d.nx * d.ny;
     nsets = d.shared_coe ? 1 : d.nbatch;
     XEE_CHECK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
@@ -366,47 +376,97 @@ struct Plan : PlanBase {
 
 template <class T>
 int Plan<T>::estimate_rho(cudaStream_t s, double* rho_out) {
-  // Work on solve slot 0 of a private pair of buffers; shared operator (or operator set 0).
+  TraceTimer tt("estimate_rho");
+  // Spectral radius rho of the Jacobi iteration matrix G = I - D^-1 L, on a homogeneous probe problem
+  // (f = 0, zero boundary) with the shared operator (or operator set 0):
+  //   stage A  power iteration from the lowest sine mode: rho_A = ||G^k e|| / ||G^(k-1) e||  (an under-estimate:
+  //            the gap to the second mode is ~1e-4, so the quotient is still a mixture after a few hundred steps);
+  //   stage B  Chebyshev probe (Hageman & Young's adaptive idea): iterate the homogeneous problem with the
+  //            Chebyshev weights of the current estimate rho_E.  Modes inside [-rho_E, rho_E] are damped at the
+  //            optimal rate exp(-acosh(1/rho_E)) per sweep, the dominant mode rho_1 > rho_E only at
+  //            exp(acosh(rho_1/rho_E) - acosh(1/rho_E)) and soon dominates, so the measured decay B over p sweeps
+  //            gives  rho_1 = rho_E * cosh(acosh(1/rho_E) + ln(B)/p).  Repeated until the correction is small.
   T *e0 = nullptr, *e1 = nullptr, *zf = nullptr;
   XEE_CHECK(cudaMalloc(&e0, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&e1, sizeof(T) * nn));
   XEE_CHECK(cudaMalloc(&zf, sizeof(T) * nn));
   XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn, s));
-  // Smooth positive start vector: product of half sines (close to the dominant mode), zero boundary.
   std::vector<T> h(nn, T(0));
   for (int j = 1; j < d.ny - 1; ++j)
     for (int i = 1; i < d.nx - 1; ++i)
       h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
   XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
   XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
-  // One-solve launch geometry.
   const int save_nb = d.nbatch, save_gz = gz, save_spb = spb;
   d.nbatch = 1; gz = 1; spb = 1;
-  const int iters_total = env_int("XEE_RHO_ITERS", 400);
-  auto norm_of = [&](const T* x, double* out) -> int {
-    // ||x||: run an APPLY-free reduction through the residual path: residual of (L x - 0) is not the
-    // norm we need, so copy to host (one small field; this runs once per operator).
+  // Norms are taken in the D-weighted inner product (D = -coe5 > 0): G = I - D^-1 L is similar to a symmetric
+  // matrix through D^(1/2) (exactly so for B = 0 or constant B), so in this norm the power-iteration quotient is a
+  // monotone UNDER-estimate of rho, which stage B then corrects upwards.
+  std::vector<T> wD(nn);
+  XEE_CHECK(cudaMemcpyAsync(wD.data(), coe + 4 * nn, sizeof(T) * nn, cudaMemcpyDeviceToHost, s));
+  auto norm_of = [&](const T* x, double* out) -> int {   // one small field, a handful of times per operator
     XEE_CHECK(cudaMemcpyAsync(h.data(), x, sizeof(T) * nn, cudaMemcpyDeviceToHost, s));
     XEE_CHECK(cudaStreamSynchronize(s));
-    double t = 0; for (size_t q = 0; q < nn; ++q) t += (double)h[q] * (double)h[q];
+    double t = 0; for (size_t q = 0; q < nn; ++q) t += std::fabs((double)wD[q]) * (double)h[q] * (double)h[q];
     *out = std::sqrt(t);
     return 0;
   };
-  double n_prev = 0, n_cur = 0, rho = 0;
-  int rc = 0;
-  for (int k = 1; k <= iters_total && !rc; ++k) {
-    const T* src = (k & 1) ? e0 : e1; T* dst = (k & 1) ? e1 : e0;
-    SweepArgs<T> a = args(src, dst, zf, T(1), T(1), nullptr);
+  int rc = 0, parity = 0;   // current iterate lives in (parity ? e1 : e0)
+  auto sweep = [&](int mode, double omega) -> int {
+    const T* src = parity ? e1 : e0; T* dst = parity ? e0 : e1;
+    SweepArgs<T> a = args(src, dst, zf, T(1), (T)omega, nullptr);
     a.nbatch = 1;
-    rc = launch_sweep(a, MODE_JACOBI, false, s);
-    if (k == iters_total - 1) rc = rc || norm_of(dst, &n_prev);
-    if (k == iters_total) rc = rc || norm_of(dst, &n_cur);
+    parity ^= 1;
+    return launch_sweep(a, mode, false, s);
+  };
+  // ---- stage A
+  const int itA = env_int("XEE_RHO_ITERS", 200);
+  double n_prev = 0, n_cur = 0;
+  for (int k = 1; k <= itA && !rc; ++k) {
+    rc = sweep(MODE_JACOBI, 1.0);
+    if (k == itA - 1) rc = rc || norm_of(parity ? e1 : e0, &n_prev);
+    if (k == itA) rc = rc || norm_of(parity ? e1 : e0, &n_cur);
+  }
+  double rho = (!rc && n_prev > 0) ? n_cur / n_prev : 0.0;
+  if (!rc && !(rho > 0.0 && rho < 1.0)) {
+    rc = fail("xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant?");
+  }
+  // ---- stage B
+  const int rounds = env_int("XEE_RHO_ROUNDS", 4), p = env_int("XEE_RHO_PROBE", 200);
+  for (int r = 0; r < rounds && !rc; ++r) {
+    // restart the Chebyshev sequence from the current iterate: x_{-1} := x_0
+    XEE_CHECK(cudaMemcpyAsync(parity ? e0 : e1, parity ? e1 : e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+    double nA = 0, nB = 0;
+    for (int k = 1; k <= 2 * p && !rc; ++k) {
+      rc = sweep(MODE_CHEBYSHEV, cheb_omega(k, rho));
+      if (k == p) rc = rc || norm_of(parity ? e1 : e0, &nA);
+      if (k == 2 * p) rc = rc || norm_of(parity ? e1 : e0, &nB);
+    }
+    if (rc || !(nA > 0) || !(nB > 0)) break;
+    // Solve  T_2p(x1)/T_p(x1) = B * T_2p(xE)/T_p(xE),  x1 = rho_1/rho_E = cosh(a), xE = 1/rho_E = cosh(o),
+    // i.e.  lncosh(2pa) - lncosh(pa) = ln B + lncosh(2po) - lncosh(po),  for a in [0, o] by bisection.
+    auto lncosh = [](double x) { return x + std::log1p(std::exp(-2.0 * x)) - M_LN2; };
+    const double lnB = std::log(nB / nA);
+    const double o = std::acosh(1.0 / rho);
+    const double target = lnB + lncosh(2.0 * p * o) - lncosh((double)p * o);
+    auto g = [&](double a) { return lncosh(2.0 * p * a) - lncosh((double)p * a) - target; };
+    if (g(0.0) >= 0.0) break;                    // decay at (or faster than) the optimal rate: rho_E already covers rho_1
+    double lo = 0.0, hi = o;
+    if (g(hi) < 0.0) hi = 4.0 * o;               // rho_1 >= 1 would mean divergence; clamp below
+    for (int itb = 0; itb < 80; ++itb) { const double mid = 0.5 * (lo + hi); (g(mid) < 0.0 ? lo : hi) = mid; }
+    const double arg = 0.5 * (lo + hi);
+    double rho_new = rho * std::cosh(arg);
+    rho_new = std::min(rho_new, 1.0 - 1e-10);
+    const double rel = std::fabs(rho_new - rho) / (1.0 - rho);
+    rho = rho_new;
+    if (rel < 0.02) break;
+    // renormalise the probe so it never underflows
+    if (nB < 1e-100) break;
   }
   d.nbatch = save_nb; gz = save_gz; spb = save_spb;
   cudaFree(e0); cudaFree(e1); cudaFree(zf);
   if (rc) return 1;
-  rho = n_prev > 0 ? n_cur / n_prev : 0.0;
-  if (!(rho > 0.0 && rho < 1.0)) return fail("xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant?");
   *rho_out = rho;
+  if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho = 1 - %.4e\n", 1.0 - rho);
   return 0;
 }
 
