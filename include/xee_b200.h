@@ -143,6 +143,8 @@ int xee_plan_sweeps_dev(xee_plan* p, void* psi_dev, const void* f_dev, double al
                         void* stream);
 /* out = L psi (interior; boundary 0) for the whole batch. */
 int xee_plan_apply_dev(xee_plan* p, const void* psi_dev, void* out_dev, void* stream);
+/* The library keeps freed field buffers (>= 1 MiB) for reuse (cap: XEE_CACHE_MB, default 16 GiB); this returns them. */
+void xee_release_cached_memory(void);
 /* Kernel-launch counter (bench.py's gpu_launches): launches issued by this library since reset. */
 long long xee_launch_count(int reset);
 /* Time (ms, CUDA events on the plan's stream) and launches of the dominant sweep kernel since reset. */

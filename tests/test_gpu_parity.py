@@ -280,3 +280,71 @@ def test_tma_kernel_matches_direct_kernel_and_oracle_bitwise(name, shape, nb):
         res[kern] = (psi.cpu().numpy(), out)
         plan.close()
     assert np.array_equal(res[1][0], res[2][0]) and list(res[1][1]["iters"]) == list(res[2][1]["iters"])
+
+
+def _run_diagnose(tmp_path, diag_txt, extra_files=(), r8=False, flag_file=None):
+    from xlab_ee_fortran_b200 import _lib
+    exe = _lib.build_diagnose()
+    A, B, C, bc = ref_test1_inputs()
+    for n, arr in (("A.bin", A), ("B.bin", B), ("C.bin", C), ("bc_init.bin", bc)) + tuple(extra_files):
+        arr.astype(np.float32).tofile(tmp_path / n)
+    if flag_file:
+        (tmp_path / flag_file).write_text("")
+    r = subprocess.run([exe] + (["--r8"] if r8 else []), input=diag_txt, capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_driver_rehost_runs_test1_end_to_end(tmp_path):
+    """BASELINE config 1 through the re-hosted driver: the reference's own diag.txt (CRLF and all) on stdin, raw
+    float32 .bin files in, the reference's output names/shapes out."""
+    torch, X, O = _mods()
+    gj = golden_json()
+    diag = gj["reference_test1_diag_txt"]
+    # (a) deterministic variant: max_iter = 1000 -> bit-identical to the golden 1000-sweep field
+    d1000 = diag.replace("100000", "1000")
+    out = _run_diagnose(tmp_path, d1000, flag_file="debug_mode_2")
+    assert "Iter:      100, err_now: " in out and " Elliptic Tools: [Error] Max iteration reached." in out
+    rchi = np.fromfile(tmp_path / "rchi-[BAROTROPIC]-O.bin", np.float32)
+    assert rchi.size == 200 * 200 and sha(rchi) == gj["test1"]["f32"]["psi1000_sha256"]
+    eta = np.fromfile(tmp_path / "eta-[BAROTROPIC]-A.bin", np.float32)
+    assert eta.size == 199 * 200
+    d = O.Domain((0.0, 1.0), (0.0, 1.0), 200, 200, 0, 0)
+    assert np.array_equal(eta.reshape(200, 199), O.cal_eta(rchi.reshape(200, 200), d))
+    A, B, C, bc = ref_test1_inputs()
+    a, b, c = O.build_abc(A, B, C, d)
+    assert np.array_equal(np.fromfile(tmp_path / "solver_a-sA.bin", np.float32).reshape(198, 199), a)
+    assert np.array_equal(np.fromfile(tmp_path / "solver_b-B.bin", np.float32).reshape(199, 199), b)
+    assert np.array_equal(np.fromfile(tmp_path / "solver_c-sC.bin", np.float32).reshape(199, 198), c)
+    assert (tmp_path / "result.txt").read_text().startswith(" Time elapsed (sec) : ")
+    # (b) the reference's own settings, to the stop rule (real(4): the stop sweep sits on the round-off floor)
+    (tmp_path / "debug_mode_2").unlink()
+    out = _run_diagnose(tmp_path, diag)
+    assert " Elliptic Tools: Iteration success." in out
+    rchi = np.fromfile(tmp_path / "rchi-[BAROTROPIC]-O.bin", np.float32).reshape(200, 200)
+    gold = gj["test1"]["f32"]
+    assert np.sqrt((rchi.astype(np.float64) ** 2).sum()) == pytest.approx(gold["psi_stop_l2"], rel=2e-4)
+    eta = np.fromfile(tmp_path / "eta-[BAROTROPIC]-A.bin", np.float32)
+    assert float(eta.max()) == pytest.approx(gold["eta_stop_max"], rel=2e-3)
+
+
+def test_driver_rehost_secondary_circulation_baro_all_r8(tmp_path):
+    """SECONDARY_CIRCULATION + BARO_ALL (+ forcing file), promoted build: both passes, u/w/rpsi outputs."""
+    torch, X, O = _mods()
+    A, B, C, bc = ref_test1_inputs()
+    forcing = (1e-3 * np.cos(np.linspace(0, 3, 200))[None, :] * np.sin(np.linspace(0, 2, 200))[:, None]).astype(np.float32)
+    diag = ("SECONDARY_CIRCULATION-CYLINDRICAL-DENSITY_BOUSSINESQ-BARO_ALL   // mode\n"
+            "0.0 2.0 0.0 1.0 // domain\n\n200 200 // grid\n. // in\n. // out\nA.bin // A\nB.bin // B\nC.bin // C\n"
+            "forcing.bin // forcing\nbc_init.bin // bc\n1e-30 1.0 300 0.9 // criteria\n")
+    out = _run_diagnose(tmp_path, diag, extra_files=(("forcing.bin", forcing),), r8=True)
+    assert out.count("Relaxation uses") == 2
+    d = O.Domain((0.0, 2.0), (0.0, 1.0), 200, 200, 1, 0)
+    g = O.geometry(d, np.float64)
+    a, b, c = O.build_abc(A.astype(np.float64), B.astype(np.float64), C.astype(np.float64), d)
+    for tag, bb in (("[BAROTROPIC]", np.zeros_like(b)), ("[BAROCLINIC]", b)):
+        coe, _ = O.cal_coe(a, bb, c, g["dr"], g["dz"], 200, 200)
+        ref = O.solve_elliptic(300, 100, 10, 5, 1e-30, 1.0, 0.9, bc.astype(np.float64), coe, forcing.astype(np.float64))
+        u, w = O.cal_uw(ref["dat"], d)
+        assert np.array_equal(np.fromfile(tmp_path / f"rpsi-{tag}-O.bin", np.float32).reshape(200, 200), ref["dat"].astype(np.float32))
+        assert np.array_equal(np.fromfile(tmp_path / f"w-{tag}-A.bin", np.float32).reshape(200, 199), w.astype(np.float32))
+        assert np.array_equal(np.fromfile(tmp_path / f"u-{tag}-C.bin", np.float32).reshape(199, 200), u.astype(np.float32))

@@ -35,6 +35,22 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+DIAGNOSE = os.path.join(_PKG, "bin", "xee_diagnose")
+
+
+def build_diagnose(force: bool = False) -> str:
+    """Host-only C++ re-host of the reference driver (csrc/xee_diagnose.cpp), linked against libxee_b200.so."""
+    src = os.path.join(CSRC, "xee_diagnose.cpp")
+    if force or not os.path.exists(DIAGNOSE) or os.path.getmtime(src) > os.path.getmtime(DIAGNOSE) or os.path.getmtime(SO) > os.path.getmtime(DIAGNOSE):
+        os.makedirs(os.path.dirname(DIAGNOSE), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O2", "-std=c++17", src, "-L" + LIBDIR, "-lxee_b200", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../lib", "-o", DIAGNOSE]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return DIAGNOSE
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> xlab_ee_fortran_b200/lib/libxee_b200.so"""
     if force or _stale():

@@ -17,6 +17,7 @@ const char* xee_last_error(void) { return g_last_error.c_str(); }
 int xee_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 const char* xee_build_info(void) { return "xee_b200 sm_100a " __DATE__ " " __TIME__; }
 long long xee_launch_count(int reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
+void xee_release_cached_memory(void) { DevPool::get().trim(0); }
 
 int xee_plan_create(const xee_plan_desc* desc, xee_plan** out) {
   PlanBase* p = nullptr;

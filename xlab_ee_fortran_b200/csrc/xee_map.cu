@@ -221,7 +221,7 @@ struct Map : MapBase {
     XEE_CHECK(cudaMalloc(&ra, sizeof(T) * nr)); XEE_CHECK(cudaMalloc(&za, sizeof(T) * nz));
     XEE_CHECK(cudaMalloc(&ex, sizeof(T) * nz)); XEE_CHECK(cudaMalloc(&rho, sizeof(T) * nz));
     XEE_CHECK(cudaMalloc(&theta, sizeof(T) * (nr - 1) * (nz - 1)));
-    XEE_CHECK(cudaMalloc(&psi, sizeof(T) * nn * nb)); XEE_CHECK(cudaMalloc(&f, sizeof(T) * nn * nb));
+    XEE_CHECK(pool_alloc(&psi, sizeof(T) * nn * nb)); XEE_CHECK(pool_alloc(&f, sizeof(T) * nn * nb));
     XEE_CHECK(cudaMalloc(&r1v, sizeof(T) * nb));
     XEE_CHECK(cudaMalloc(&heat_d, sizeof(Heat) * nb)); XEE_CHECK(cudaMalloc(&integ, sizeof(double) * 3 * nb));
     XEE_CHECK(cudaMemcpyAsync(ra, h_ra.data(), sizeof(T) * nr, cudaMemcpyHostToDevice, s));
@@ -264,7 +264,7 @@ struct Map : MapBase {
     TraceTimer tt("map destroy");
     delete pl; delete pl1;
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ra); cudaFree(za); cudaFree(ex); cudaFree(rho); cudaFree(theta);
-    cudaFree(eta); cudaFree(chi); cudaFree(fchi); cudaFree(psi); cudaFree(f); cudaFree(r1v); cudaFree(heat_d); cudaFree(integ);
+    cudaFree(eta); cudaFree(chi); cudaFree(fchi); pool_free(psi); pool_free(f); cudaFree(r1v); cudaFree(heat_d); cudaFree(integ);
   }
 
   // table row: iters, r1, err, sum_Q, ke_gen=(g0/theta0) I[w theta], eff=ke_gen/sum_Q, sum_Qeta, eff_eta=sum_Qeta/sum_Q

@@ -7,6 +7,7 @@
 #include <ctime>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,6 +43,50 @@ inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+
+// Caching device allocator for the large field buffers: cudaFree of GiB-sized blocks costs tens of ms
+// (unmap + implicit sync), which a driver that creates a plan per solve_elliptic call would pay every time.
+// Freed blocks are kept (exact-size match) up to XEE_CACHE_MB (default 16384) and reused.
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  std::map<void*, size_t> live;
+  size_t cached = 0;
+  static DevPool& get() { static DevPool p; return p; }
+  cudaError_t alloc(void** out, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find(bytes);
+      if (it != free_blocks.end()) { *out = it->second; cached -= bytes; free_blocks.erase(it); live[*out] = bytes; return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) { trim(0); e = cudaMalloc(out, bytes); }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = bytes; }
+    return e;
+  }
+  void release(void* p) {
+    if (!p) return;
+    size_t bytes = 0;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = live.find(p);
+      if (it == live.end()) { cudaFree(p); return; }
+      bytes = it->second; live.erase(it);
+      const size_t cap = (size_t)env_int("XEE_CACHE_MB", 16384) << 20;
+      if (bytes >= (1u << 20) && cached + bytes <= cap) { free_blocks.emplace(bytes, p); cached += bytes; return; }
+    }
+    cudaFree(p);
+  }
+  void trim(size_t keep) {
+    std::lock_guard<std::mutex> g(mu);
+    while (cached > keep && !free_blocks.empty()) {
+      auto it = std::prev(free_blocks.end());
+      cudaFree(it->second); cached -= it->first; free_blocks.erase(it);
+    }
+  }
+};
+template <class P> inline cudaError_t pool_alloc(P** out, size_t bytes) { return DevPool::get().alloc((void**)out, bytes); }
+inline void pool_free(void* p) { DevPool::get().release(p); }
 
 // XEE_TRACE=1: wall-clock phase timings on stderr (host side, after a device sync).
 struct TraceTimer {
@@ -93,9 +138,9 @@ struct Plan : PlanBase {
     nn = (size_t)d.nx * d.ny;
     nsets = d.shared_coe ? 1 : d.nbatch;
     XEE_CHECK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
-    XEE_CHECK(cudaMalloc(&coe, sizeof(T) * kPlanes * nn * nsets));
+    XEE_CHECK(pool_alloc(&coe, sizeof(T) * kPlanes * nn * nsets));
     XEE_CHECK(cudaMemset(coe, 0, sizeof(T) * kPlanes * nn * nsets));
-    XEE_CHECK(cudaMalloc(&x1, sizeof(T) * nn * d.nbatch));
+    XEE_CHECK(pool_alloc(&x1, sizeof(T) * nn * d.nbatch));
     const int nb = d.nbatch;
     XEE_CHECK(cudaMalloc(&st.done, sizeof(int) * nb)); XEE_CHECK(cudaMalloc(&st.iters, sizeof(int) * nb));
     XEE_CHECK(cudaMalloc(&st.ccnt, sizeof(int) * nb)); XEE_CHECK(cudaMalloc(&st.lcnt, sizeof(int) * nb));
@@ -189,7 +234,7 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    cudaFree(coe); cudaFree(x1); cudaFree(io_psi); cudaFree(io_f); cudaFree(partial);
+    pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); cudaFree(partial);
     cudaFree(st.done); cudaFree(st.iters); cudaFree(st.ccnt); cudaFree(st.lcnt); cudaFree(st.errb);
     cudaFree(st.err_before); cudaFree(st.err_now); cudaFree(st.ratio); cudaFree(st.r1); cudaFree(st.r2);
     cudaFree(st.active); cudaFree(st.trace_err); cudaFree(st.trace_ratio);
@@ -478,7 +523,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   T* x0 = (T*)psi;
   const T* fd = (const T*)f;
   if (host_io) {
-    if (!io_psi) { XEE_CHECK(cudaMalloc(&io_psi, fbytes)); XEE_CHECK(cudaMalloc(&io_f, fbytes)); }
+    if (!io_psi) { XEE_CHECK(pool_alloc(&io_psi, fbytes)); XEE_CHECK(pool_alloc(&io_f, fbytes)); }
     XEE_CHECK(cudaMemcpyAsync(io_psi, psi, fbytes, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(io_f, f, fbytes, cudaMemcpyHostToDevice, s));
     x0 = io_psi; fd = io_f;
