@@ -231,13 +231,19 @@ def run_ours(args):
     hheat = torch.from_numpy(my).pin_memory()
 
     def e2e_step():
+        ts = [time.perf_counter()]
         mm = EfficiencyMap(hA.numpy(), hB.numpy(), hC.numpy(), LR, LZ, nloc, "f64", arith=args.arith, method=args.method,
                            r1_rel=R1_REL, device=local)
+        ts.append(time.perf_counter())
         t = mm.run(hheat.numpy(), prm)
+        ts.append(time.perf_counter())
         mm.close()
-        if world > 1:
-            return gather_rows(torch.from_numpy(t).cuda(), total)
-        return t
+        ts.append(time.perf_counter())
+        out = gather_rows(torch.from_numpy(t).cuda(), total) if world > 1 else t
+        ts.append(time.perf_counter())
+        if os.environ.get("XEE_TRACE"):
+            print(f"[rank {rank}] e2e step: create {1e3*(ts[1]-ts[0]):.1f} run {1e3*(ts[2]-ts[1]):.1f} close {1e3*(ts[3]-ts[2]):.1f} gather {1e3*(ts[4]-ts[3]):.1f} ms", file=sys.stderr, flush=True)
+        return out
 
     e2e = None
     if args.e2e_steps > 0:

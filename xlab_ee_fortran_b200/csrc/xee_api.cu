@@ -69,9 +69,9 @@ template <class T> constexpr int dtype_of() { return sizeof(T) == 4 ? XEE_F32 : 
 template <class T>
 struct DevBuf {
   T* p = nullptr; size_t n = 0;
-  explicit DevBuf(size_t n_) : n(n_) { if (cudaMalloc(&p, sizeof(T) * (n ? n : 1)) != cudaSuccess) { g_last_error = "cudaMalloc"; die("DevBuf"); } }
+  explicit DevBuf(size_t n_) : n(n_) { if (pool_alloc(&p, sizeof(T) * (n ? n : 1)) != cudaSuccess) { g_last_error = "cudaMalloc"; die("DevBuf"); } }
   DevBuf(const T* host, size_t n_) : DevBuf(n_) { if (cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "H2D"; die("DevBuf"); } }
-  ~DevBuf() { cudaFree(p); }
+  ~DevBuf() { pool_free(p); }
   void to_host(T* host) const { if (cudaMemcpy(host, p, sizeof(T) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { g_last_error = "D2H"; die("DevBuf"); } }
 };
 

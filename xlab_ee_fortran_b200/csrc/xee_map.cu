@@ -217,20 +217,20 @@ struct Map : MapBase {
     pl = new Plan<T>(); pl->d = pd;
     if (pl->init()) return 1;
     cudaStream_t s = pl->own_stream;
-    XEE_CHECK(cudaMalloc(&A, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&B, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&C, sizeof(T) * nn));
-    XEE_CHECK(cudaMalloc(&ra, sizeof(T) * nr)); XEE_CHECK(cudaMalloc(&za, sizeof(T) * nz));
-    XEE_CHECK(cudaMalloc(&ex, sizeof(T) * nz)); XEE_CHECK(cudaMalloc(&rho, sizeof(T) * nz));
-    XEE_CHECK(cudaMalloc(&theta, sizeof(T) * (nr - 1) * (nz - 1)));
+    XEE_CHECK(pool_alloc(&A, sizeof(T) * nn)); XEE_CHECK(pool_alloc(&B, sizeof(T) * nn)); XEE_CHECK(pool_alloc(&C, sizeof(T) * nn));
+    XEE_CHECK(pool_alloc(&ra, sizeof(T) * nr)); XEE_CHECK(pool_alloc(&za, sizeof(T) * nz));
+    XEE_CHECK(pool_alloc(&ex, sizeof(T) * nz)); XEE_CHECK(pool_alloc(&rho, sizeof(T) * nz));
+    XEE_CHECK(pool_alloc(&theta, sizeof(T) * (nr - 1) * (nz - 1)));
     XEE_CHECK(pool_alloc(&psi, sizeof(T) * nn * nb)); XEE_CHECK(pool_alloc(&f, sizeof(T) * nn * nb));
-    XEE_CHECK(cudaMalloc(&r1v, sizeof(T) * nb));
-    XEE_CHECK(cudaMalloc(&heat_d, sizeof(Heat) * nb)); XEE_CHECK(cudaMalloc(&integ, sizeof(double) * 3 * nb));
+    XEE_CHECK(pool_alloc(&r1v, sizeof(T) * nb));
+    XEE_CHECK(pool_alloc(&heat_d, sizeof(Heat) * nb)); XEE_CHECK(pool_alloc(&integ, sizeof(double) * 3 * nb));
     XEE_CHECK(cudaMemcpyAsync(ra, h_ra.data(), sizeof(T) * nr, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(za, h_za.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(ex, h_ex.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(rho, h_rho.data(), sizeof(T) * nz, cudaMemcpyHostToDevice, s));
     // inputs arrive in the reference's file format: headerless float32, i fastest (field_tools.f90:30-52)
     float* stage = nullptr;
-    XEE_CHECK(cudaMalloc(&stage, sizeof(float) * nn * 3));
+    XEE_CHECK(pool_alloc(&stage, sizeof(float) * nn * 3));
     XEE_CHECK(cudaMemcpyAsync(stage, hA, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(stage + nn, hB, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(stage + 2 * nn, hC, sizeof(float) * nn, cudaMemcpyHostToDevice, s));
@@ -240,8 +240,8 @@ struct Map : MapBase {
     f32_to_T_kernel<T><<<gb, 256, 0, s>>>(stage + 2 * nn, C, nn); XEE_LAUNCH_OK();
     // K1 + K2 (cylindrical: rcuva = ra)
     T *a = nullptr, *b = nullptr, *c = nullptr;
-    XEE_CHECK(cudaMalloc(&a, sizeof(T) * (nr - 1) * (nz - 2))); XEE_CHECK(cudaMalloc(&b, sizeof(T) * (nr - 1) * (nz - 1)));
-    XEE_CHECK(cudaMalloc(&c, sizeof(T) * (nr - 2) * (nz - 1)));
+    XEE_CHECK(pool_alloc(&a, sizeof(T) * (nr - 1) * (nz - 2))); XEE_CHECK(pool_alloc(&b, sizeof(T) * (nr - 1) * (nz - 1)));
+    XEE_CHECK(pool_alloc(&c, sizeof(T) * (nr - 2) * (nz - 1)));
     dim3 blk(64, 4), g((nr + 63) / 64, (nz + 3) / 4);
     build_abc_kernel<T><<<g, blk, 0, s>>>(A, B, C, ra, rho, a, b, c, nr, nz); XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(s));
@@ -253,18 +253,18 @@ struct Map : MapBase {
       if (pl1->init()) return 1;
       XEE_CHECK(cudaStreamSynchronize(s));
       if (pl1->set_abc(a, b, c, (double)dr, (double)dz)) return 1;
-      XEE_CHECK(cudaMalloc(&eta, sizeof(T) * (nr - 1) * nz)); XEE_CHECK(cudaMalloc(&chi, sizeof(T) * nn));
-      XEE_CHECK(cudaMalloc(&fchi, sizeof(T) * nn));
+      XEE_CHECK(pool_alloc(&eta, sizeof(T) * (nr - 1) * nz)); XEE_CHECK(pool_alloc(&chi, sizeof(T) * nn));
+      XEE_CHECK(pool_alloc(&fchi, sizeof(T) * nn));
     }
     XEE_CHECK(cudaStreamSynchronize(s));
-    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(stage);
+    pool_free(a); pool_free(b); pool_free(c); pool_free(stage);
     return 0;
   }
   ~Map() override {
     TraceTimer tt("map destroy");
     delete pl; delete pl1;
-    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ra); cudaFree(za); cudaFree(ex); cudaFree(rho); cudaFree(theta);
-    cudaFree(eta); cudaFree(chi); cudaFree(fchi); pool_free(psi); pool_free(f); cudaFree(r1v); cudaFree(heat_d); cudaFree(integ);
+    pool_free(A); pool_free(B); pool_free(C); pool_free(ra); pool_free(za); pool_free(ex); pool_free(rho); pool_free(theta);
+    pool_free(eta); pool_free(chi); pool_free(fchi); pool_free(psi); pool_free(f); pool_free(r1v); pool_free(heat_d); pool_free(integ);
   }
 
   // table row: iters, r1, err, sum_Q, ke_gen=(g0/theta0) I[w theta], eff=ke_gen/sum_Q, sum_Qeta, eff_eta=sum_Qeta/sum_Q
@@ -292,13 +292,13 @@ struct Map : MapBase {
       xee_solve_params p1 = *prm_in;
       T* r1c = nullptr;
       if (d.r1_rel_rms_f > 0) {
-        XEE_CHECK(cudaMalloc(&r1c, sizeof(T)));
+        XEE_CHECK(pool_alloc(&r1c, sizeof(T)));
         rms_interior_kernel<T><<<1, 256, 0, s>>>(fchi, nr, nz, (T)d.r1_rel_rms_f, r1c); XEE_LAUNCH_OK();
         p1.r1 = 1.0; p1.r1_per_solve = r1c;
       }
       int it1, e1; double a1, a2;
       const int rc = pl1->solve(chi, fchi, &p1, &it1, &a1, &a2, &e1, s, false, nullptr, 0);
-      if (r1c) cudaFree(r1c);
+      if (r1c) pool_free(r1c);
       if (rc) return 1;
       dim3 ge((nr - 1 + 127) / 128, nz, 1);
       eta_kernel<T><<<ge, 128, 0, s>>>(chi, eta, ra, ra, rho, ex, nr, nz, k.g0, k.Cp, k.theta0); XEE_LAUNCH_OK();

@@ -46,34 +46,39 @@ inline int env_int(const char* name, int dflt) {
 
 // Caching device allocator for the large field buffers: cudaFree of GiB-sized blocks costs tens of ms
 // (unmap + implicit sync), which a driver that creates a plan per solve_elliptic call would pay every time.
-// Freed blocks are kept (exact-size match) up to XEE_CACHE_MB (default 16384) and reused.
+// cudaMalloc/cudaFree are also erratic (an occasional cudaFree was measured at 0.2-1.6 s on a busy box), so EVERY
+// device allocation of the library goes through this pool.  Freed blocks are kept (exact-size match) up to
+// XEE_CACHE_MB (default 16384) and reused; xee_release_cached_memory() returns them to the driver.
 struct DevPool {
   std::mutex mu;
-  std::multimap<size_t, void*> free_blocks;
-  std::map<void*, size_t> live;
+  typedef std::pair<int, size_t> Key;            // (device, bytes): blocks never migrate between devices
+  std::multimap<Key, void*> free_blocks;
+  std::map<void*, Key> live;
   size_t cached = 0;
   static DevPool& get() { static DevPool p; return p; }
   cudaError_t alloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const Key key(dev, bytes);
     {
       std::lock_guard<std::mutex> g(mu);
-      auto it = free_blocks.find(bytes);
-      if (it != free_blocks.end()) { *out = it->second; cached -= bytes; free_blocks.erase(it); live[*out] = bytes; return cudaSuccess; }
+      auto it = free_blocks.find(key);
+      if (it != free_blocks.end()) { *out = it->second; cached -= bytes; free_blocks.erase(it); live[*out] = key; return cudaSuccess; }
     }
     cudaError_t e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) { trim(0); e = cudaMalloc(out, bytes); }
-    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = bytes; }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = key; }
     return e;
   }
   void release(void* p) {
     if (!p) return;
-    size_t bytes = 0;
     {
       std::lock_guard<std::mutex> g(mu);
       auto it = live.find(p);
       if (it == live.end()) { cudaFree(p); return; }
-      bytes = it->second; live.erase(it);
+      const Key key = it->second; live.erase(it);
       const size_t cap = (size_t)env_int("XEE_CACHE_MB", 16384) << 20;
-      if (bytes >= (1u << 20) && cached + bytes <= cap) { free_blocks.emplace(bytes, p); cached += bytes; return; }
+      if (cached + key.second <= cap) { free_blocks.emplace(key, p); cached += key.second; return; }
     }
     cudaFree(p);
   }
@@ -81,7 +86,7 @@ struct DevPool {
     std::lock_guard<std::mutex> g(mu);
     while (cached > keep && !free_blocks.empty()) {
       auto it = std::prev(free_blocks.end());
-      cudaFree(it->second); cached -= it->first; free_blocks.erase(it);
+      cudaFree(it->second); cached -= it->first.second; free_blocks.erase(it);
     }
   }
 };
@@ -142,15 +147,15 @@ struct Plan : PlanBase {
     XEE_CHECK(cudaMemset(coe, 0, sizeof(T) * kPlanes * nn * nsets));
     XEE_CHECK(pool_alloc(&x1, sizeof(T) * nn * d.nbatch));
     const int nb = d.nbatch;
-    XEE_CHECK(cudaMalloc(&st.done, sizeof(int) * nb)); XEE_CHECK(cudaMalloc(&st.iters, sizeof(int) * nb));
-    XEE_CHECK(cudaMalloc(&st.ccnt, sizeof(int) * nb)); XEE_CHECK(cudaMalloc(&st.lcnt, sizeof(int) * nb));
-    XEE_CHECK(cudaMalloc(&st.errb, sizeof(int) * nb));
-    XEE_CHECK(cudaMalloc(&st.err_before, sizeof(T) * nb)); XEE_CHECK(cudaMalloc(&st.err_now, sizeof(T) * nb));
-    XEE_CHECK(cudaMalloc(&st.ratio, sizeof(T) * nb)); XEE_CHECK(cudaMalloc(&st.r1, sizeof(T) * nb));
-    XEE_CHECK(cudaMalloc(&st.r2, sizeof(T) * nb)); XEE_CHECK(cudaMalloc(&st.active, sizeof(int)));
+    XEE_CHECK(pool_alloc(&st.done, sizeof(int) * nb)); XEE_CHECK(pool_alloc(&st.iters, sizeof(int) * nb));
+    XEE_CHECK(pool_alloc(&st.ccnt, sizeof(int) * nb)); XEE_CHECK(pool_alloc(&st.lcnt, sizeof(int) * nb));
+    XEE_CHECK(pool_alloc(&st.errb, sizeof(int) * nb));
+    XEE_CHECK(pool_alloc(&st.err_before, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.err_now, sizeof(T) * nb));
+    XEE_CHECK(pool_alloc(&st.ratio, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.r1, sizeof(T) * nb));
+    XEE_CHECK(pool_alloc(&st.r2, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.active, sizeof(int)));
     st.trace_cap = 4096;
-    XEE_CHECK(cudaMalloc(&st.trace_err, sizeof(T) * st.trace_cap));
-    XEE_CHECK(cudaMalloc(&st.trace_ratio, sizeof(T) * st.trace_cap));
+    XEE_CHECK(pool_alloc(&st.trace_err, sizeof(T) * st.trace_cap));
+    XEE_CHECK(pool_alloc(&st.trace_ratio, sizeof(T) * st.trace_cap));
     XEE_CHECK(cudaMallocHost(&h_active, sizeof(int) * 4));
     for (auto& e : poll_ev) XEE_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // launch geometry of the direct kernel
@@ -164,7 +169,7 @@ struct Plan : PlanBase {
       while (spb > 1 && (long long)ntiles * ((d.nbatch + spb - 1) / spb) < 148LL * 8 * 4) spb /= 2;
     }
     gz = (d.nbatch + spb - 1) / spb;
-    XEE_CHECK(cudaMalloc(&partial, sizeof(double) * (size_t)ntiles * nb));
+    XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)ntiles * nb));
     int dev = 0;
     XEE_CHECK(cudaGetDevice(&dev));
     XEE_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -234,14 +239,17 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); cudaFree(partial);
-    cudaFree(st.done); cudaFree(st.iters); cudaFree(st.ccnt); cudaFree(st.lcnt); cudaFree(st.errb);
-    cudaFree(st.err_before); cudaFree(st.err_now); cudaFree(st.ratio); cudaFree(st.r1); cudaFree(st.r2);
-    cudaFree(st.active); cudaFree(st.trace_err); cudaFree(st.trace_ratio);
-    if (h_active) cudaFreeHost(h_active);
-    for (auto& e : poll_ev) if (e) cudaEventDestroy(e);
-    for (auto& e : ev_pool) cudaEventDestroy(e);
-    if (own_stream) cudaStreamDestroy(own_stream);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); }
+    { TraceTimer t("  ~Plan: small cudaFree");
+      pool_free(partial);
+      pool_free(st.done); pool_free(st.iters); pool_free(st.ccnt); pool_free(st.lcnt); pool_free(st.errb);
+      pool_free(st.err_before); pool_free(st.err_now); pool_free(st.ratio); pool_free(st.r1); pool_free(st.r2);
+      pool_free(st.active); pool_free(st.trace_err); pool_free(st.trace_ratio); }
+    { TraceTimer t("  ~Plan: cudaFreeHost"); if (h_active) cudaFreeHost(h_active); }
+    { TraceTimer t("  ~Plan: events+stream");
+      for (auto& e : poll_ev) if (e) cudaEventDestroy(e);
+      for (auto& e : ev_pool) cudaEventDestroy(e);
+      if (own_stream) cudaStreamDestroy(own_stream); }
   }
 
   int set_coe_aos(const void* src, bool on_host) override {
@@ -249,7 +257,7 @@ struct Plan : PlanBase {
     const T* dev = (const T*)src;
     T* tmp = nullptr;
     if (on_host) {
-      XEE_CHECK(cudaMalloc(&tmp, bytes));
+      XEE_CHECK(pool_alloc(&tmp, bytes));
       XEE_CHECK(cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, own_stream));
       dev = tmp;
     }
@@ -257,7 +265,7 @@ struct Plan : PlanBase {
     aos_to_planar_kernel<T><<<g, 128, 0, own_stream>>>(dev, coe, d.nx, d.ny);
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
-    if (tmp) cudaFree(tmp);
+    if (tmp) pool_free(tmp);
     cheb_rho = 0.0;
     return 0;
   }
@@ -276,14 +284,14 @@ struct Plan : PlanBase {
   int coe_to_aos_host(void* coe_host) override {  // set 0 only (Fortran-facing cal_coe)
     T* tmp = nullptr;
     const size_t bytes = sizeof(T) * 9 * nn;
-    XEE_CHECK(cudaMalloc(&tmp, bytes));
+    XEE_CHECK(pool_alloc(&tmp, bytes));
     dim3 g((d.nx + 127) / 128, d.ny, 1);
     planar_to_aos_kernel<T><<<g, 128, 0, own_stream>>>(coe, tmp, d.nx, d.ny);
     XEE_LAUNCH_OK();
     std::vector<T> stage(9 * nn);
     XEE_CHECK(cudaMemcpyAsync(stage.data(), tmp, bytes, cudaMemcpyDeviceToHost, own_stream));
     XEE_CHECK(cudaStreamSynchronize(own_stream));
-    cudaFree(tmp);
+    pool_free(tmp);
     // interior only: the reference never writes coe's boundary entries (elliptic_tools.f90:35-36)
     T* out = (T*)coe_host;
     for (int j = 1; j < d.ny - 1; ++j)
@@ -432,8 +440,8 @@ int Plan<T>::estimate_rho(cudaStream_t s, double* rho_out) {
   //            exp(acosh(rho_1/rho_E) - acosh(1/rho_E)) and soon dominates, so the measured decay B over p sweeps
   //            gives  rho_1 = rho_E * cosh(acosh(1/rho_E) + ln(B)/p).  Repeated until the correction is small.
   T *e0 = nullptr, *e1 = nullptr, *zf = nullptr;
-  XEE_CHECK(cudaMalloc(&e0, sizeof(T) * nn)); XEE_CHECK(cudaMalloc(&e1, sizeof(T) * nn));
-  XEE_CHECK(cudaMalloc(&zf, sizeof(T) * nn));
+  XEE_CHECK(pool_alloc(&e0, sizeof(T) * nn)); XEE_CHECK(pool_alloc(&e1, sizeof(T) * nn));
+  XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn));
   XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn, s));
   std::vector<T> h(nn, T(0));
   for (int j = 1; j < d.ny - 1; ++j)
@@ -508,7 +516,7 @@ int Plan<T>::estimate_rho(cudaStream_t s, double* rho_out) {
     if (nB < 1e-100) break;
   }
   d.nbatch = save_nb; gz = save_gz; spb = save_spb;
-  cudaFree(e0); cudaFree(e1); cudaFree(zf);
+  pool_free(e0); pool_free(e1); pool_free(zf);
   if (rc) return 1;
   *rho_out = rho;
   if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho = 1 - %.4e\n", 1.0 - rho);
