@@ -348,3 +348,29 @@ def test_driver_rehost_secondary_circulation_baro_all_r8(tmp_path):
         assert np.array_equal(np.fromfile(tmp_path / f"rpsi-{tag}-O.bin", np.float32).reshape(200, 200), ref["dat"].astype(np.float32))
         assert np.array_equal(np.fromfile(tmp_path / f"w-{tag}-A.bin", np.float32).reshape(200, 199), w.astype(np.float32))
         assert np.array_equal(np.fromfile(tmp_path / f"u-{tag}-C.bin", np.float32).reshape(199, 200), u.astype(np.float32))
+
+
+def test_chebyshev_with_one_operator_per_solve():
+    """Time-series shape (BASELINE config 5): every solve has its own operator, hence its own Jacobi spectral
+    radius; the Chebyshev weights are computed per solve inside the kernel."""
+    torch, X, O = _mods()
+    nx, ny, nb = 96, 64, 5
+    rng = np.random.default_rng(21)
+    coes, F, P = [], [], []
+    for k in range(nb):
+        a, b, c, f, x0 = _rand_case(nx, ny, np.float64, seed=100 + k, bscale=0.02)
+        coes.append(O.cal_coe(a * (1 + 0.5 * k), b, c * (1 + 2.0 * (nb - k)), 1.0, 0.7, nx, ny)[0]); F.append(f); P.append(x0)
+    coe = np.stack(coes); F = np.stack(F); P = np.stack(P)
+    rms_f = np.sqrt((F[:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2)))
+    plan = X.Plan(nx, ny, nbatch=nb, dtype="f64", shared_coe=False, arith="fast", method="chebyshev")
+    plan.set_coe_aos(coe)
+    psi = torch.from_numpy(P.copy()).cuda(); ft = torch.from_numpy(F).cuda()
+    r1 = torch.from_numpy(1e-11 * rms_f).cuda()
+    out = plan.solve(psi, ft, X.SolveParams(max_iter=100000, check_step=50, converge_time=2, r1=1.0, r2=0.0, r1_per_solve=r1))
+    assert np.all(out["err"] == 0)
+    got = psi.cpu().numpy()
+    for k in range(nb):
+        ref = O.solve_elliptic(400000, 100, 2, 5, 1e-11 * rms_f[k], 0.0, 1.0, P[k], coe[k], F[k])
+        assert ref["err"] == 0 and rel_l2(got[k], ref["dat"]) < 1e-8
+        assert out["iters"][k] * 4 < ref["max_iter"]
+    print("per-solve chebyshev sweeps", out["iters"])

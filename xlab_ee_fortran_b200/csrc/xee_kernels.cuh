@@ -125,7 +125,9 @@ struct SweepArgs {
   long long field_stride;    // nx*ny
   int nx, ny, nbatch, spb;   // spb = solves handled by one block (operator kept in registers)
   T alpha;         // Jacobi weight
-  T omega;         // Chebyshev weight of this sweep (1 on the first sweep)
+  T omega;         // Chebyshev weight of this sweep (1 on the first sweep); used when rho_ps == NULL
+  const T* rho_ps; // per-solve Jacobi spectral radius (one operator per solve): omega computed in-kernel
+  int cheb_k;      // index of this sweep in the Chebyshev sequence (1, 2, ...)
   const int* done; // per-solve stop flags (NULL = none)
   double* partial; // [n][ntiles] sum of r^2 per tile (check sweeps only)
   int ntiles;
@@ -133,6 +135,15 @@ struct SweepArgs {
 };
 
 enum { MODE_JACOBI = 0, MODE_CHEBYSHEV = 1, MODE_APPLY = 2 };
+
+// Chebyshev weight of sweep k for Jacobi spectral radius rho:  omega_1 = 1,
+// omega_k = 2 T_{k-1}(1/rho) / (rho T_k(1/rho)), in the stable ratio form with q = 1/rho - sqrt(1/rho^2 - 1).
+__host__ __device__ inline double cheb_omega(int k, double rho) {
+  if (k <= 1) return 1.0;
+  const double sg = 1.0 / rho, q = sg - sqrt(sg * sg - 1.0);
+  const double q2k = pow(q, 2.0 * (k - 1));
+  return (2.0 / rho) * q * (1.0 + q2k) / (1.0 + q2k * q * q);
+}
 
 constexpr int kDirBX = 64, kDirBY = 4;
 
@@ -184,9 +195,10 @@ __global__ void __launch_bounds__(kDirBX* kDirBY) sweep_direct_kernel(const Swee
       if (MODE == MODE_JACOBI) {
         *d = jacobi_update<T, ARITH>(p[4], r, a.alpha, c[4], rcp);
       } else {  // Chebyshev-accelerated Jacobi: x+ = omega*(xJ - x-) + x-
+        const T om = a.rho_ps ? (T)cheb_omega(a.cheb_k, (double)a.rho_ps[n]) : a.omega;
         const T xj = jacobi_update<T, ARITH>(p[4], r, T(1), c[4], rcp);
         const T xm = *d;
-        *d = R::fma(a.omega, xj - xm, xm);
+        *d = R::fma(om, xj - xm, xm);
       }
     }
     if (CHECK) {
@@ -195,6 +207,20 @@ __global__ void __launch_bounds__(kDirBX* kDirBY) sweep_direct_kernel(const Swee
       if (tid == 0) a.partial[(size_t)n * a.ntiles + blockIdx.y * gridDim.x + blockIdx.x] = tot;
     }
   }
+}
+
+// D-weighted norm per solve, sqrt(sum |coe5| x^2), for the spectral-radius probe (one block per solve).
+template <class T>
+__global__ void __launch_bounds__(256) wnorm_kernel(const T* __restrict__ x, const T* __restrict__ coe,
+                                                    long long coe_set_stride, long long nn, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int n = blockIdx.x;
+  const T* xp = x + (size_t)n * nn;
+  const T* w = coe + (size_t)n * coe_set_stride + 4 * nn;
+  double s = 0;
+  for (long long q = threadIdx.x; q < nn; q += 256) s += fabs((double)w[q]) * (double)xp[q] * (double)xp[q];
+  const double t = block_sum(s, red, threadIdx.x, 8);
+  if (threadIdx.x == 0) out[n] = sqrt(t);
 }
 
 // Per-solve control state of solve_elliptic (elliptic_tools.f90:160-164, 201-233).

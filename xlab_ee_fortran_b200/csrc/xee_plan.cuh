@@ -131,7 +131,9 @@ struct Plan : PlanBase {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   cudaEvent_t poll_ev[4]{};
-  double cheb_rho = 0.0;
+  double cheb_rho = 0.0;             // shared operator: one spectral radius
+  std::vector<double> rho_ps;        // one operator per solve: per-solve spectral radii (host copy)
+  T* rho_dev = nullptr;              //   ... and on the device
   // v2 (TMA) sweep kernel: launch geometry + tensor maps of the buffers of the current call
   bool use_tma = false;
   int tma_tiles_x = 0, tma_tiles_y = 0, tma_chunk = 1, tma_nchunks = 1, tma_grid = 1, tma_nstage = 6, num_sms = 148;
@@ -239,7 +241,7 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); }
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
       pool_free(st.done); pool_free(st.iters); pool_free(st.ccnt); pool_free(st.lcnt); pool_free(st.errb);
@@ -266,7 +268,7 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     if (tmp) pool_free(tmp);
-    cheb_rho = 0.0;
+    cheb_rho = 0.0; rho_ps.clear();
     return 0;
   }
   int set_abc(const void* a, const void* b, const void* c, double dx, double dy) override {
@@ -278,7 +280,7 @@ struct Plan : PlanBase {
                                                  d.ny, sa, sb, sc, (long long)kPlanes * nn);
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
-    cheb_rho = 0.0;
+    cheb_rho = 0.0; rho_ps.clear();
     return 0;
   }
   int coe_to_aos_host(void* coe_host) override {  // set 0 only (Fortran-facing cal_coe)
@@ -306,6 +308,7 @@ struct Plan : PlanBase {
     a.field_stride = (long long)nn;
     a.nx = d.nx; a.ny = d.ny; a.nbatch = d.nbatch; a.spb = spb;
     a.alpha = alpha; a.omega = omega; a.done = done; a.partial = partial; a.ntiles = sweep_ntiles();
+    a.rho_ps = nullptr; a.cheb_k = 1;
     return a;
   }
 
@@ -370,15 +373,6 @@ struct Plan : PlanBase {
     ev_used = 0;
   }
 
-  // Chebyshev weight of sweep k (k = 1,2,...) for Jacobi spectral radius rho:
-  //   omega_1 = 1, omega_{k+1} = 2 T_k(1/rho) / (rho T_{k+1}(1/rho)), evaluated in the stable ratio form.
-  static double cheb_omega(int k, double rho) {
-    if (k <= 1) return 1.0;
-    const double sg = 1.0 / rho, q = sg - std::sqrt(sg * sg - 1.0);
-    const double q2k = std::pow(q, 2.0 * (k - 1));
-    return (2.0 / rho) * q * (1.0 + q2k) / (1.0 + q2k * q * q);
-  }
-
   int apply(const void* psi, void* out, cudaStream_t s) override {
     SweepArgs<T> a = args((const T*)psi, nullptr, nullptr, T(1), T(1), nullptr);
     a.apply_out = (T*)out;
@@ -388,7 +382,20 @@ struct Plan : PlanBase {
 
   // Power iteration on the Jacobi iteration matrix G = I - D^-1 L (homogeneous problem, zero
   // boundary): rho ~ ||G^{k+1} e|| / ||G^k e||.  Uses x1 and a scratch batch of size 1.
-  int estimate_rho(cudaStream_t s, double* rho_out);
+  int estimate_rho(cudaStream_t s);
+  // Make the Chebyshev parameters of this call available: explicit value, cached estimate, or a fresh estimate.
+  int prepare_cheb(double rho_given, cudaStream_t s) {
+    if (rho_given > 0) {
+      cheb_rho = rho_given; rho_ps.assign(nsets, rho_given);
+      if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * nsets));
+      std::vector<T> h(nsets, (T)rho_given);
+      XEE_CHECK(cudaMemcpyAsync(rho_dev, h.data(), sizeof(T) * nsets, cudaMemcpyHostToDevice, s));
+      XEE_CHECK(cudaStreamSynchronize(s));
+      return 0;
+    }
+    if (cheb_rho > 0 && (int)rho_ps.size() == nsets) return 0;
+    return estimate_rho(s);
+  }
 
   int sweeps(void* psi, const void* f, double alpha, int nsw, double* rms, cudaStream_t s) override {
     T* x0 = (T*)psi;
@@ -397,12 +404,14 @@ struct Plan : PlanBase {
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
     const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
-    if (mode == MODE_CHEBYSHEV && cheb_rho <= 0 && estimate_rho(s, &cheb_rho)) return 1;
+    if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;
     for (int cnt = 1; cnt <= nsw; ++cnt) {
       const T* src = (cnt & 1) ? x0 : x1;
       T* dst = (cnt & 1) ? x1 : x0;
       const double om = mode == MODE_CHEBYSHEV ? cheb_omega(cnt, cheb_rho) : 1.0;
-      if (launch_sweep(args(src, dst, (const T*)f, (T)alpha, (T)om, nullptr), mode, rms && cnt == nsw, s)) return 1;
+      SweepArgs<T> a = args(src, dst, (const T*)f, (T)alpha, (T)om, nullptr);
+      if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
+      if (launch_sweep(a, mode, rms && cnt == nsw, s)) return 1;
     }
     sweep_launches += nsw;
     XEE_CHECK(cudaEventRecord(e1, s));
@@ -428,98 +437,104 @@ struct Plan : PlanBase {
 };
 
 template <class T>
-int Plan<T>::estimate_rho(cudaStream_t s, double* rho_out) {
+int Plan<T>::estimate_rho(cudaStream_t s) {
   TraceTimer tt("estimate_rho");
-  // Spectral radius rho of the Jacobi iteration matrix G = I - D^-1 L, on a homogeneous probe problem
-  // (f = 0, zero boundary) with the shared operator (or operator set 0):
-  //   stage A  power iteration from the lowest sine mode: rho_A = ||G^k e|| / ||G^(k-1) e||  (an under-estimate:
-  //            the gap to the second mode is ~1e-4, so the quotient is still a mixture after a few hundred steps);
+  // Spectral radius rho of the Jacobi iteration matrix G = I - D^-1 L of every operator set (1 for a shared
+  // operator, nbatch for one operator per solve), on homogeneous probe problems (f = 0, zero boundary):
+  //   stage A  power iteration from the lowest sine mode: rho_A = ||G^k e|| / ||G^(k-1) e||.  Norms are taken in
+  //            the D-weighted inner product (D = -coe5 > 0): G is similar to a symmetric matrix through D^(1/2)
+  //            (exactly so for B = 0 or constant B), so the quotient is a monotone UNDER-estimate of rho;
   //   stage B  Chebyshev probe (Hageman & Young's adaptive idea): iterate the homogeneous problem with the
   //            Chebyshev weights of the current estimate rho_E.  Modes inside [-rho_E, rho_E] are damped at the
-  //            optimal rate exp(-acosh(1/rho_E)) per sweep, the dominant mode rho_1 > rho_E only at
-  //            exp(acosh(rho_1/rho_E) - acosh(1/rho_E)) and soon dominates, so the measured decay B over p sweeps
-  //            gives  rho_1 = rho_E * cosh(acosh(1/rho_E) + ln(B)/p).  Repeated until the correction is small.
-  T *e0 = nullptr, *e1 = nullptr, *zf = nullptr;
-  XEE_CHECK(pool_alloc(&e0, sizeof(T) * nn)); XEE_CHECK(pool_alloc(&e1, sizeof(T) * nn));
-  XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn));
-  XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn, s));
+  //            optimal rate, the dominant mode rho_1 > rho_E more slowly, so it soon dominates and the measured
+  //            decay B between sweeps p and 2p gives rho_1 from  T_2p(x1)/T_p(x1) = B T_2p(xE)/T_p(xE),
+  //            x1 = rho_1/rho_E, xE = 1/rho_E.  Repeated until the correction is below 2 % of 1 - rho.
+  const int ns = nsets;
+  T *e0 = nullptr, *e1 = nullptr, *zf = nullptr; double* nrm_d = nullptr;
+  XEE_CHECK(pool_alloc(&e0, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&e1, sizeof(T) * nn * ns));
+  XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&nrm_d, sizeof(double) * ns));
+  if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * ns));
+  XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn * ns, s));
   std::vector<T> h(nn, T(0));
   for (int j = 1; j < d.ny - 1; ++j)
     for (int i = 1; i < d.nx - 1; ++i)
       h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
-  XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-  XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+  for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+  XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+  // probe launch geometry: `ns` solves through the direct kernel
   const int save_nb = d.nbatch, save_gz = gz, save_spb = spb;
-  d.nbatch = 1; gz = 1; spb = 1;
-  // Norms are taken in the D-weighted inner product (D = -coe5 > 0): G = I - D^-1 L is similar to a symmetric
-  // matrix through D^(1/2) (exactly so for B = 0 or constant B), so in this norm the power-iteration quotient is a
-  // monotone UNDER-estimate of rho, which stage B then corrects upwards.
-  std::vector<T> wD(nn);
-  XEE_CHECK(cudaMemcpyAsync(wD.data(), coe + 4 * nn, sizeof(T) * nn, cudaMemcpyDeviceToHost, s));
-  auto norm_of = [&](const T* x, double* out) -> int {   // one small field, a handful of times per operator
-    XEE_CHECK(cudaMemcpyAsync(h.data(), x, sizeof(T) * nn, cudaMemcpyDeviceToHost, s));
+  d.nbatch = ns; spb = 1; gz = ns;
+  std::vector<double> nA(ns), nB(ns), rho(ns, 0.0);
+  std::vector<T> rho_h(ns);
+  auto norms = [&](const T* x, std::vector<double>& out) -> int {
+    wnorm_kernel<T><<<ns, 256, 0, s>>>(x, coe, d.shared_coe ? 0 : (long long)kPlanes * nn, (long long)nn, nrm_d);
+    XEE_LAUNCH_OK();
+    XEE_CHECK(cudaMemcpyAsync(out.data(), nrm_d, sizeof(double) * ns, cudaMemcpyDeviceToHost, s));
     XEE_CHECK(cudaStreamSynchronize(s));
-    double t = 0; for (size_t q = 0; q < nn; ++q) t += std::fabs((double)wD[q]) * (double)h[q] * (double)h[q];
-    *out = std::sqrt(t);
     return 0;
   };
   int rc = 0, parity = 0;   // current iterate lives in (parity ? e1 : e0)
-  auto sweep = [&](int mode, double omega) -> int {
+  auto sweep = [&](int mode, int k) -> int {
     const T* src = parity ? e1 : e0; T* dst = parity ? e0 : e1;
-    SweepArgs<T> a = args(src, dst, zf, T(1), (T)omega, nullptr);
-    a.nbatch = 1;
+    SweepArgs<T> a = args(src, dst, zf, T(1), T(1), nullptr);
+    a.nbatch = ns; a.rho_ps = rho_dev; a.cheb_k = k;
     parity ^= 1;
     return launch_sweep(a, mode, false, s);
   };
   // ---- stage A
   const int itA = env_int("XEE_RHO_ITERS", 200);
-  double n_prev = 0, n_cur = 0;
   for (int k = 1; k <= itA && !rc; ++k) {
-    rc = sweep(MODE_JACOBI, 1.0);
-    if (k == itA - 1) rc = rc || norm_of(parity ? e1 : e0, &n_prev);
-    if (k == itA) rc = rc || norm_of(parity ? e1 : e0, &n_cur);
+    rc = sweep(MODE_JACOBI, 1);
+    if (k == itA - 1) rc = rc || norms(parity ? e1 : e0, nA);
+    if (k == itA) rc = rc || norms(parity ? e1 : e0, nB);
   }
-  double rho = (!rc && n_prev > 0) ? n_cur / n_prev : 0.0;
-  if (!rc && !(rho > 0.0 && rho < 1.0)) {
-    rc = fail("xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant?");
+  for (int n = 0; n < ns && !rc; ++n) {
+    rho[n] = nA[n] > 0 ? nB[n] / nA[n] : 0.0;
+    if (!(rho[n] > 0.0 && rho[n] < 1.0)) rc = fail("xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant?");
   }
   // ---- stage B
   const int rounds = env_int("XEE_RHO_ROUNDS", 4), p = env_int("XEE_RHO_PROBE", 200);
+  std::vector<char> settled(ns, 0);
+  auto lncosh = [](double x) { return x + std::log1p(std::exp(-2.0 * x)) - M_LN2; };
   for (int r = 0; r < rounds && !rc; ++r) {
+    for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];
+    XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
     // restart the Chebyshev sequence from the current iterate: x_{-1} := x_0
-    XEE_CHECK(cudaMemcpyAsync(parity ? e0 : e1, parity ? e1 : e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
-    double nA = 0, nB = 0;
+    XEE_CHECK(cudaMemcpyAsync(parity ? e0 : e1, parity ? e1 : e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
     for (int k = 1; k <= 2 * p && !rc; ++k) {
-      rc = sweep(MODE_CHEBYSHEV, cheb_omega(k, rho));
-      if (k == p) rc = rc || norm_of(parity ? e1 : e0, &nA);
-      if (k == 2 * p) rc = rc || norm_of(parity ? e1 : e0, &nB);
+      rc = sweep(MODE_CHEBYSHEV, k);
+      if (k == p) rc = rc || norms(parity ? e1 : e0, nA);
+      if (k == 2 * p) rc = rc || norms(parity ? e1 : e0, nB);
     }
-    if (rc || !(nA > 0) || !(nB > 0)) break;
-    // Solve  T_2p(x1)/T_p(x1) = B * T_2p(xE)/T_p(xE),  x1 = rho_1/rho_E = cosh(a), xE = 1/rho_E = cosh(o),
-    // i.e.  lncosh(2pa) - lncosh(pa) = ln B + lncosh(2po) - lncosh(po),  for a in [0, o] by bisection.
-    auto lncosh = [](double x) { return x + std::log1p(std::exp(-2.0 * x)) - M_LN2; };
-    const double lnB = std::log(nB / nA);
-    const double o = std::acosh(1.0 / rho);
-    const double target = lnB + lncosh(2.0 * p * o) - lncosh((double)p * o);
-    auto g = [&](double a) { return lncosh(2.0 * p * a) - lncosh((double)p * a) - target; };
-    if (g(0.0) >= 0.0) break;                    // decay at (or faster than) the optimal rate: rho_E already covers rho_1
-    double lo = 0.0, hi = o;
-    if (g(hi) < 0.0) hi = 4.0 * o;               // rho_1 >= 1 would mean divergence; clamp below
-    for (int itb = 0; itb < 80; ++itb) { const double mid = 0.5 * (lo + hi); (g(mid) < 0.0 ? lo : hi) = mid; }
-    const double arg = 0.5 * (lo + hi);
-    double rho_new = rho * std::cosh(arg);
-    rho_new = std::min(rho_new, 1.0 - 1e-10);
-    const double rel = std::fabs(rho_new - rho) / (1.0 - rho);
-    rho = rho_new;
-    if (rel < 0.02) break;
-    // renormalise the probe so it never underflows
-    if (nB < 1e-100) break;
+    if (rc) break;
+    bool all_settled = true;
+    for (int n = 0; n < ns; ++n) {
+      if (settled[n]) continue;
+      if (!(nA[n] > 1e-280) || !(nB[n] > 1e-280)) { settled[n] = 1; continue; }
+      const double rE = (double)rho_h[n];          // the value the device actually used
+      const double o = std::acosh(1.0 / rE);
+      const double target = std::log(nB[n] / nA[n]) + lncosh(2.0 * p * o) - lncosh((double)p * o);
+      auto g = [&](double a) { return lncosh(2.0 * p * a) - lncosh((double)p * a) - target; };
+      if (g(0.0) >= 0.0) { settled[n] = 1; continue; }   // decays at the optimal rate: rho_E already covers rho_1
+      double lo = 0.0, hi = o;
+      if (g(hi) < 0.0) hi = 4.0 * o;
+      for (int itb = 0; itb < 80; ++itb) { const double mid = 0.5 * (lo + hi); (g(mid) < 0.0 ? lo : hi) = mid; }
+      const double rho_new = std::min(rE * std::cosh(0.5 * (lo + hi)), 1.0 - 1e-10);
+      const double rel = std::fabs(rho_new - rE) / (1.0 - rE);
+      rho[n] = rho_new;
+      if (rel < 0.02) settled[n] = 1; else all_settled = false;
+    }
+    if (all_settled) break;
   }
   d.nbatch = save_nb; gz = save_gz; spb = save_spb;
-  pool_free(e0); pool_free(e1); pool_free(zf);
+  pool_free(e0); pool_free(e1); pool_free(zf); pool_free(nrm_d);
   if (rc) return 1;
-  *rho_out = rho;
-  if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho = 1 - %.4e\n", 1.0 - rho);
+  rho_ps = rho;
+  for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];
+  XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
+  XEE_CHECK(cudaStreamSynchronize(s));
+  cheb_rho = rho[0];
+  if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho[0] = 1 - %.4e (%d operator set%s)\n", 1.0 - rho[0], ns, ns > 1 ? "s" : "");
   return 0;
 }
 
@@ -542,8 +557,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   const int max_iter = prm->max_iter;
   const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
   if (mode == MODE_CHEBYSHEV) {
-    if (prm->rho_jacobi > 0) cheb_rho = prm->rho_jacobi;
-    else if (cheb_rho <= 0 && estimate_rho(s, &cheb_rho)) return 1;
+    if (prepare_cheb(prm->rho_jacobi, s)) return 1;
   }
   init_state_kernel<T><<<(nb + 127) / 128, 128, 0, s>>>(st, nb, (T)prm->r1, (T)prm->r2, (const T*)prm->r1_per_solve);
   XEE_LAUNCH_OK();
@@ -567,7 +581,9 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
       T* dst = (cnt & 1) ? x1 : x0;
       const bool check = (cnt % check_step) == 0;                                // :179-183
       const double om = mode == MODE_CHEBYSHEV ? cheb_omega(cnt, cheb_rho) : 1.0;
-      if (launch_sweep(args(src, dst, fd, (T)prm->alpha, (T)om, st.done), mode, check, s)) return 1;
+      SweepArgs<T> a = args(src, dst, fd, (T)prm->alpha, (T)om, st.done);
+      if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
+      if (launch_sweep(a, mode, check, s)) return 1;
     }
     sweep_launches += chunk;
     XEE_CHECK(cudaEventRecord(e1, s));
