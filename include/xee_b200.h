@@ -188,6 +188,29 @@ int xee_map_run_dev(xee_map* m, const double* heat_dev, const xee_solve_params* 
 int xee_map_get_field(xee_map* m, int which, void* host_out);
 int xee_map_sweep_kernel_stats(xee_map* m, double* ms_total, long long* launches, int reset);
 
+/* =====================================================================================
+ * Part 4 - time-series diagnosis (BASELINE config 5): one vortex snapshot = one operator per
+ * solve; thermal + dynamical source term (src/old-diagnose/diagnose.f90:383-436), Ekman-pumping
+ * bottom boundary condition (xtt-lib-python/XPumping.py:79-90), vortex fields built on the device
+ * from wind-profile parameters (xtt-lib-python/XWindProfile.py:10-23).  Cylindrical geometry.
+ * ===================================================================================== */
+#define XEE_SERIES_PARAMS 21 /* doubles per snapshot: f0, f_core, f_env, radius, konst1, H, N2, pump r0 r1 r2,
+                                pump c00 c01 c10 c11, heat r_c z_c sigma_r sigma_z Q0, friction k, friction h */
+typedef struct xee_series xee_series;
+typedef struct xee_series_desc {
+  int dtype, nr, nz, nsnap, density_mode, arith, method, device;
+  double Lr[2], Lz[2];
+  double r1_rel_rms_f; /* >0: per-snapshot tolerance r1_n = r1_rel * rms(f_n) */
+} xee_series_desc;
+int xee_series_create(const xee_series_desc* desc, xee_series** out);
+int xee_series_destroy(xee_series* s);
+/* params: HOST [nsnap][XEE_SERIES_PARAMS]; table: HOST [nsnap][XEE_MAP_COLS] =
+ * iters, r1, err, sum_Q, ke_gen, efficiency, max|w|, max|u| */
+int xee_series_run_host(xee_series* s, const double* params_host, const xee_solve_params* prm, double* table_host);
+/* which: 0 psi, 1 f, 2 theta_B, 3 u (C grid), 4 w (A grid), 5 A, 6 B, 7 C, 8 m2 (B grid); all [nsnap][...], plan dtype */
+int xee_series_get_field(xee_series* s, int which, void* host_out);
+int xee_series_sweep_kernel_stats(xee_series* s, double* ms_total, long long* launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""GPU parity of the time-series chain (BASELINE config 5: one operator per snapshot, thermal + dynamical source
+term, pumping boundary condition, device-side vortex builder) against the oracle composition."""
+import numpy as np
+import pytest
+
+from tests.series_oracle import series_rows
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _f32_close(a, b):
+    """Device-built fields go through float32 like the reference's files: allow a last-bit difference."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= 1.3e-7 * np.maximum(np.abs(a), np.abs(b)))
+
+
+def test_series_matches_oracle():
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.time_series import TimeSeries
+    nr, nz, ns = 64, 40, 4
+    Lr, Lz = (0.0, 6.0e5), (0.0, 1.5e4)
+    params = W.series_params(ns)
+    kw = dict(max_iter=2000000, check_step=100, converge_time=2, r1_rel=1e-11)
+    ref = series_rows(params, nr, nz, Lr, Lz, np.float64, kw)
+    ts = TimeSeries(nr, nz, Lr, Lz, ns, "f64", arith="fast", method="chebyshev", r1_rel=1e-11)
+    tab = ts.run(params, X.SolveParams(max_iter=400000, check_step=50, converge_time=2, r1=1.0, r2=0.0))
+    for name in ("A", "B", "C"):
+        assert _f32_close(ts.field(name), ref[name]), name            # device vortex builder
+    # feed the oracle's float32 fields? no: compare the downstream chain at tolerance (inputs may differ in 1 f32 ulp)
+    assert rel_l2(ts.field("m2"), ref["m2"]) < 1e-6
+    assert rel_l2(ts.field("f"), ref["f"]) < 1e-6
+    assert np.all(tab[:, 2] == 0) and np.all(tab[:, 0] * 4 < ref["table"][:, 0])
+    psi = ts.field("psi")
+    assert np.array_equal(psi[:, 0, :], ref["psi"][:, 0, :])             # pumping boundary row: bitwise
+    assert np.all(psi[:, -1, :] == 0) and np.all(psi[:, :, 0] == 0) and np.all(psi[:, :, -1] == 0)
+    for n in range(ns):
+        assert rel_l2(psi[n], ref["psi"][n]) < 2e-6                      # limited by the 1-ulp(f32) input differences
+    assert np.allclose(tab[:, 3], ref["table"][:, 3], rtol=1e-12)
+    assert np.allclose(tab[:, 5], ref["table"][:, 5], rtol=1e-5)
+    assert np.allclose(tab[:, 6], ref["table"][:, 6], rtol=1e-5) and np.allclose(tab[:, 7], ref["table"][:, 7], rtol=1e-5)
+    print("snapshots: sweeps", tab[:, 0], "efficiency", tab[:, 5], "max|w|", tab[:, 6])
+
+
+def test_series_exact_chain_on_identical_inputs():
+    """Same chain with the oracle fed the DEVICE-built A,B,C (so inputs are identical): north_star tolerances."""
+    import xlab_ee_fortran_b200 as X
+    from oracle import numpy_ref as N
+    from oracle import oracle as O
+    from tests.map_oracle import background_theta, heat_field
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.time_series import TimeSeries
+    nr, nz, ns = 48, 36, 2
+    Lr, Lz = (0.0, 5.0e5), (0.0, 1.4e4)
+    dt = np.float64
+    params = W.series_params(ns, total=9, first=3)
+    ts = TimeSeries(nr, nz, Lr, Lz, ns, "f64", arith="strict", method="jacobi", r1_rel=1e-10)
+    tab = ts.run(params, X.SolveParams(max_iter=2000000, check_step=100, converge_time=2, r1=1.0, r2=0.0))
+    A, B, C = ts.field("A"), ts.field("B"), ts.field("C")
+    d = O.Domain(Lr, Lz, nr, nz, 0, 0); g = O.geometry(d, dt); k = N.constants(dt)
+    for n in range(ns):
+        a, b, c = O.build_abc(A[n], B[n], C[n], d)
+        coe, _ = O.cal_coe(a, b, c, g["dr"], g["dz"], nr, nz)
+        _, _, _, rhoC_C = O.stagger_averages(A[n], B[n], C[n], d)
+        m2 = O.angular_momentum_sq(rhoC_C, d)
+        assert rel_l2(ts.field("m2")[n], m2) < 1e-14
+        _, _, _, bottom, F = W.series_fields_host(params[n], nr, nz, Lr, Lz)
+        f = O.rhs_thermal(heat_field(params[n][14:19], g, dt), d)[1] + O.rhs_momentum(m2, F, d)
+        assert rel_l2(ts.field("f")[n], f) < 1e-12
+        fdev = ts.field("f")[n]
+        psi0 = np.zeros((nz, nr)); psi0[0] = bottom
+        rms = float(np.sqrt((fdev[1:-1, 1:-1] ** 2).mean()))
+        r = O.solve_elliptic(2000000, 100, 2, 5, 1e-10 * rms, 0.0, 1.0, psi0, coe, fdev)
+        assert r["max_iter"] == tab[n, 0] and r["err"] == 0              # strict Jacobi on identical inputs: same sweep count
+        assert np.array_equal(ts.field("psi")[n], r["dat"])              # ... and bit-identical field
+        u, w = O.cal_uw(r["dat"], d)
+        assert np.array_equal(ts.field("u")[n], u) and np.array_equal(ts.field("w")[n], w)
+        assert np.array_equal(ts.field("theta")[n], background_theta(A[n], B[n], C[n], d, dt))
+        ke = O.integrate_weight_B(O.cal_wtheta(w, ts.field("theta")[n], d), d) * float(k["g0"]) / float(k["theta0"])
+        assert tab[n, 4] == pytest.approx(ke, rel=1e-9)

@@ -27,6 +27,11 @@ __global__ void build_abc_kernel(const T* __restrict__ A, const T* __restrict__ 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0-based i-1
   const int j = blockIdx.y * blockDim.y + threadIdx.y;  // 0-based j-1
   if (i >= nr || j >= nz) return;
+  {  // blockIdx.z = field set (time series: one vortex per snapshot)
+    const size_t z = blockIdx.z;
+    A += z * (size_t)nr * nz; B += z * (size_t)nr * nz; C += z * (size_t)nr * nz;
+    a += z * (size_t)(nr - 1) * (nz - 2); b += z * (size_t)(nr - 1) * (nz - 1); c += z * (size_t)(nr - 2) * (nz - 1);
+  }
   const size_t o = (size_t)j * nr + i;
   if (i < nr - 1 && j < nz - 2) {  // a(i,j) = (A(i,j+1)+A(i+1,j+1))/(rc(i)+rc(i+1))/rho(j+1)
     T v = R::add(A[o + nr], A[o + nr + 1]);

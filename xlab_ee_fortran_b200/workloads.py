@@ -96,3 +96,77 @@ def test1_style_fields(nr, nz):
     A = np.ones((nz, nr), np.float32); C = np.ones((nz, nr), np.float32)
     B = (1e-2 * np.sin(2.0 * np.pi * rr) * np.sin(3.0 * np.pi * zz)).astype(np.float32)
     return A, B, C
+
+
+class Pumping:
+    """xtt-lib-python/XPumping.py:32-103 restated: piecewise-quadratic Ekman pumping rho*w(r) on [r0,r1,r2] and its
+    integral r*psi(r), used as the bottom boundary condition of r*psi (BASELINE config 5)."""
+
+    def __init__(self, rho_w0, r_arr):
+        if len(r_arr) != 3:
+            raise Exception("The length of r array must be exactly 3, the input length is %d" % (len(r_arr),))
+        self.rho_w0 = float(rho_w0); self.r_arr = np.array(r_arr, float)
+        r0, r1, r2 = self.r_arr
+        self.coe = np.zeros((2, 2))
+        self.coe[0][0] = -4.0 * self.rho_w0 / (r1 - r0) ** 2.0                     # XPumping.py:61
+        self.coe[0][1] = -self.coe[0][0] * self.int_part(r0, r0, r1)               # :62
+        a = np.array([[self.int_part(r2, r1, r2), 1.0], [self.int_part(r1, r1, r2), 1.0]])
+        b = np.array([0.0, self.coe[0][0] * self.int_part(r1, r0, r1) + self.coe[0][1]])
+        self.coe[1][0], self.coe[1][1] = np.linalg.solve(a, b)                     # :65-76
+
+    @staticmethod
+    def int_part(at_r, r_min, r_max):                                              # :40-41
+        return (at_r ** 4.0) / 4.0 - (r_min + r_max) / 3.0 * (at_r ** 3.0) + r_min * r_max * (at_r ** 2.0) / 2.0
+
+    def getRPsi(self, r):                                                          # :79-90
+        r = np.asarray(r, float); r0, r1, r2 = self.r_arr
+        inner = self.coe[0][0] * self.int_part(r, r0, r1) + self.coe[0][1]
+        outer = self.coe[1][0] * self.int_part(r, r1, r2) + self.coe[1][1]
+        return np.where(r <= r0, 0.0, np.where(r <= r1, inner, np.where(r <= r2, outer, 0.0)))
+
+    def getRhoW(self, r):                                                          # :92-103
+        r = np.asarray(r, float); r0, r1, r2 = self.r_arr
+        inner = self.coe[0][0] * (r - r0) * (r - r1); outer = self.coe[1][0] * (r - r1) * (r - r2)
+        return np.where(r <= r0, 0.0, np.where(r <= r1, inner, np.where(r <= r2, outer, 0.0)))
+
+    def getTotalFlux(self):                                                        # :48-49
+        r0, r1, _ = self.r_arr
+        return self.coe[0][0] * (self.int_part(r1, r0, r1) - self.int_part(r0, r0, r1))
+
+
+# ---- BASELINE config 5: time series of synthetic vortex snapshots (SURVEY section 8d)
+SERIES_COLS = ("f0", "f_core", "f_env", "radius", "konst1", "H", "N2", "pump_r0", "pump_r1", "pump_r2", "pump_c00",
+               "pump_c01", "pump_c10", "pump_c11", "heat_rc", "heat_zc", "heat_sr", "heat_sz", "heat_q0", "fric_k", "fric_h")
+
+
+def series_params(n_snap, total=None, first=0):
+    """[n_snap, 21] rows (SERIES_COLS) for snapshots first..first+n_snap-1 of a `total`-long series:
+    core vorticity 1e-3*(0.5+s), ring radius 5e4*(1.5-0.5 s), pumping 0.01*(1+s), s = n/(total-1);
+    heating blob and friction F = -k v(r) exp(-z/h) fixed."""
+    total = total or n_snap
+    out = np.zeros((n_snap, len(SERIES_COLS)))
+    for q in range(n_snap):
+        s = (first + q) / max(total - 1, 1)
+        f0, f_env = 5e-5, 5e-5
+        f_core = 1.0e-3 * (0.5 + s); radius = 5.0e4 * (1.5 - 0.5 * s)
+        wp = WindProfile(f0, [f_core, f_env], [radius])
+        pm = Pumping(0.01 * (1.0 + s), [0.0, 5e4, 2e5])
+        out[q] = [f0, f_core, f_env, radius, wp.konst[1], 1.0e4, 1.0e-4, *pm.r_arr, pm.coe[0][0], pm.coe[0][1], pm.coe[1][0],
+                  pm.coe[1][1], 4.0e4, 5.0e3, 1.0e4, 2.0e3, 3.5 * 287.0 * 10.0 / 86400.0, 1e-5, 1.0e3]
+    return out
+
+
+def series_fields_host(row, nr, nz, Lr, Lz):
+    """Host (numpy) statement of what the device builders compute for one snapshot row:
+    A, B, C (float32, as files), bottom boundary r*psi(r, z=Lz0) (float64, O grid row 0) and F on B (float64)."""
+    p = dict(zip(SERIES_COLS, row))
+    A, B, C = vortex_fields(nr, nz, Lr, Lz, f0=p["f0"], f_arr=(p["f_core"], p["f_env"]), radius_arr=(p["radius"],), H=p["H"],
+                            N2=p["N2"], thermal_wind_consistent=False)
+    r = np.linspace(Lr[0], Lr[1], nr); z = np.linspace(Lz[0], Lz[1], nz)
+    pm = Pumping.__new__(Pumping)
+    pm.r_arr = np.array([p["pump_r0"], p["pump_r1"], p["pump_r2"]]); pm.coe = np.array([[p["pump_c00"], p["pump_c01"]], [p["pump_c10"], p["pump_c11"]]])
+    bottom = pm.getRPsi(r)
+    wp = WindProfile(p["f0"], [p["f_core"], p["f_env"]], [p["radius"]])
+    rm = 0.5 * (r[:-1] + r[1:]); zm = 0.5 * (z[:-1] + z[1:])
+    F = -p["fric_k"] * wp.getWind(rm)[None, :] * np.exp(-zm / p["fric_h"])[:, None]
+    return A, B, C, bottom, F
