@@ -25,6 +25,9 @@ extern "C" {
 /* elliptic_tools.f90:3-4 — public error bits of the `err` bitmask */
 #define XEE_ERR_OVER_MAX_ITERATION 1
 #define XEE_ERR_EXPLODE 2
+/* Not in the reference (batched API only, opt-in through xee_solve_params.stall_checks): the residual stopped
+ * improving before r1 was reached - the solve sits on its round-off floor. */
+#define XEE_ERR_STALLED 4
 
 /* =====================================================================================
  * Part 1 — drop-in for `module elliptic_tools` (+ the driver's FD post-processing)
@@ -117,6 +120,8 @@ typedef struct xee_solve_params {
   double rho_jacobi;        /* Chebyshev only: spectral-radius estimate, <=0 = estimate   */
   int detect_explode;       /* 1: non-finite residual sets XEE_ERR_EXPLODE and stops      */
   int sync_every;           /* host polls the active-solve count every N checks (>=1)     */
+  int stall_checks;         /* >0: stop (XEE_ERR_STALLED) when the best residual has not improved by 0.1 %
+                               for this many consecutive checks; 0 = reference semantics (off)             */
 } xee_solve_params;
 
 const char* xee_last_error(void);
@@ -200,7 +205,7 @@ typedef struct xee_series xee_series;
 typedef struct xee_series_desc {
   int dtype, nr, nz, nsnap, density_mode, arith, method, device;
   double Lr[2], Lz[2];
-  double r1_rel_rms_f; /* >0: per-snapshot tolerance r1_n = r1_rel * rms(f_n) */
+  double r1_rel_rms_f; /* >0: per-snapshot tolerance r1_n = r1_rel * rms(L psi0_n - f_n), the initial residual */
 } xee_series_desc;
 int xee_series_create(const xee_series_desc* desc, xee_series** out);
 int xee_series_destroy(xee_series* s);

@@ -26,7 +26,8 @@ def series_rows(params, nr, nz, Lr, Lz, dt, solve_kw):
         f_mom = O.rhs_momentum(m2, F.astype(dt), d)
         f = f_thm + f_mom
         psi0 = np.zeros((nz, nr), dt); psi0[0, :] = bottom.astype(dt)
-        rms = float(np.sqrt((f[1:-1, 1:-1].astype(np.float64) ** 2).mean()))
+        r0 = O.do_elliptic(psi0, coe) - f                                   # tolerance relative to the initial residual
+        rms = float(np.sqrt((r0[1:-1, 1:-1].astype(np.float64) ** 2).mean()))
         r = O.solve_elliptic(solve_kw["max_iter"], solve_kw["check_step"], solve_kw["converge_time"], 5,
                              dt(solve_kw["r1_rel"] * rms), 0.0, 1.0, psi0, coe, f)
         u, w = O.cal_uw(r["dat"], d)

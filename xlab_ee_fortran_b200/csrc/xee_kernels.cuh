@@ -233,6 +233,7 @@ template <class T>
 struct SolveState {
   int* done; int* iters; int* ccnt; int* lcnt; int* errb;
   T* err_before; T* err_now; T* ratio; T* r1; T* r2;
+  T* best_err; int* stall;   // stagnation detector (opt-in, not in the reference)
   int* active;          // solves still iterating
   T* trace_err; T* trace_ratio; int trace_cap;   // solve 0 only (debug prints)
 };
@@ -248,6 +249,7 @@ __global__ void init_state_kernel(SolveState<T> st, int nbatch, T r1, T r2, cons
   st.done[n] = 0; st.iters[n] = 0; st.ccnt[n] = 0; st.lcnt[n] = 0; st.errb[n] = 0;
   st.err_before[n] = Rn<T>::huge();   // :163
   st.err_now[n] = T(0); st.ratio[n] = T(0);
+  st.best_err[n] = Rn<T>::huge(); st.stall[n] = 0;
   if (n == 0) *st.active = nbatch;
 }
 
@@ -256,7 +258,7 @@ template <class T>
 __global__ void __launch_bounds__(128) finalize_check_kernel(SolveState<T> st, const double* __restrict__ partial,
                                                              int ntiles, int ninterior, int cnt, int check_idx,
                                                              int converge_time, int lost_rate, int max_iter,
-                                                             int detect_explode) {
+                                                             int detect_explode, int stall_checks) {
   using R = Rn<T>;
   __shared__ double red[32];
   const int n = blockIdx.x;
@@ -282,6 +284,10 @@ __global__ void __launch_bounds__(128) finalize_check_kernel(SolveState<T> st, c
     if (lcnt >= lost_rate) { ccnt -= 1; lcnt = 0; }
   }
   if (detect_explode && !(err_now == err_now && R::abs(err_now) <= R::huge())) { stop = true; errb |= XEE_ERR_EXPLODE; }
+  if (stall_checks > 0 && !stop) {   // opt-in: the residual sits on its round-off floor above r1
+    if (err_now < st.best_err[n] * T(0.999)) { st.best_err[n] = err_now; st.stall[n] = 0; }
+    else if (++st.stall[n] >= stall_checks) { stop = true; errb |= XEE_ERR_STALLED; }
+  }
   st.err_before[n] = err_now;                                                     // :233
   st.err_now[n] = err_now; st.ratio[n] = ratio;
   if (cnt == max_iter) { stop = true; errb |= XEE_ERR_OVER_MAX_ITERATION; }       // :242-244

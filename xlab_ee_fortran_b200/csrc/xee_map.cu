@@ -127,8 +127,12 @@ struct Map : MapBase {
     }
     std::vector<int> iters(nb), err(nb);
     std::vector<double> r1o(nb), r2o(nb);
-    if (pl->solve(psi, f, &prm, iters.data(), r1o.data(), r2o.data(), err.data(), s, false, nullptr, 0)) return 1;
+    {
+      TraceTimer t1("  map: batched solve");
+      if (pl->solve(psi, f, &prm, iters.data(), r1o.data(), r2o.data(), err.data(), s, false, nullptr, 0)) return 1;
+    }
     if (d.adjoint_check) {
+      TraceTimer t2("  map: adjoint chi solve + eta");
       dim3 g1((nr + 127) / 128, nz, 1);
       rhs_from_B_kernel<T><<<g1, 128, 0, s>>>(B, fchi, nr, nz); XEE_LAUNCH_OK();
       XEE_CHECK(cudaMemsetAsync(chi, 0, sizeof(T) * nn, s));

@@ -152,6 +152,21 @@ __global__ void f32_to_T_kernel(const float* __restrict__ in, T* __restrict__ ou
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) out[q] = (T)in[q];
 }
+// out[n] = scale * rms over the interior of (x - y): the initial residual L psi0 - f of a solve.
+template <class T>
+__global__ void rms_diff_interior_kernel(const T* __restrict__ x, const T* __restrict__ y, int nr, int nz, T scale,
+                                         T* __restrict__ out) {
+  __shared__ double red[32];
+  const T* p = x + (size_t)blockIdx.x * nr * nz;
+  const T* q = y + (size_t)blockIdx.x * nr * nz;
+  double s = 0;
+  for (int k = threadIdx.x; k < nr * nz; k += 256) {
+    const int i = k % nr, j = k / nr;
+    if (i > 0 && i < nr - 1 && j > 0 && j < nz - 1) { const double dv = (double)p[k] - (double)q[k]; s += dv * dv; }
+  }
+  const double t = block_sum(s, red, threadIdx.x, 8);
+  if (threadIdx.x == 0) out[blockIdx.x] = (T)(sqrt(t / ((double)(nr - 2) * (nz - 2))) * (double)scale);
+}
 template <class T>
 __global__ void rms_interior_kernel(const T* __restrict__ f, int nr, int nz, T scale, T* __restrict__ out) {
   __shared__ double red[32];

@@ -155,6 +155,7 @@ struct Plan : PlanBase {
     XEE_CHECK(pool_alloc(&st.err_before, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.err_now, sizeof(T) * nb));
     XEE_CHECK(pool_alloc(&st.ratio, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.r1, sizeof(T) * nb));
     XEE_CHECK(pool_alloc(&st.r2, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.active, sizeof(int)));
+    XEE_CHECK(pool_alloc(&st.best_err, sizeof(T) * nb)); XEE_CHECK(pool_alloc(&st.stall, sizeof(int) * nb));
     st.trace_cap = 4096;
     XEE_CHECK(pool_alloc(&st.trace_err, sizeof(T) * st.trace_cap));
     XEE_CHECK(pool_alloc(&st.trace_ratio, sizeof(T) * st.trace_cap));
@@ -246,7 +247,7 @@ struct Plan : PlanBase {
       pool_free(partial);
       pool_free(st.done); pool_free(st.iters); pool_free(st.ccnt); pool_free(st.lcnt); pool_free(st.errb);
       pool_free(st.err_before); pool_free(st.err_now); pool_free(st.ratio); pool_free(st.r1); pool_free(st.r2);
-      pool_free(st.active); pool_free(st.trace_err); pool_free(st.trace_ratio); }
+      pool_free(st.active); pool_free(st.trace_err); pool_free(st.trace_ratio); pool_free(st.best_err); pool_free(st.stall); }
     { TraceTimer t("  ~Plan: cudaFreeHost"); if (h_active) cudaFreeHost(h_active); }
     { TraceTimer t("  ~Plan: events+stream");
       for (auto& e : poll_ev) if (e) cudaEventDestroy(e);
@@ -589,7 +590,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     XEE_CHECK(cudaEventRecord(e1, s));
     if ((cnt % check_step) == 0) {
       finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
-                                                  lost_rate, max_iter, prm->detect_explode);
+                                                  lost_rate, max_iter, prm->detect_explode, prm->stall_checks);
       XEE_LAUNCH_OK();
       const int slot = check_idx & 3;
       XEE_CHECK(cudaMemcpyAsync(&h_active[slot], st.active, sizeof(int), cudaMemcpyDeviceToHost, s));

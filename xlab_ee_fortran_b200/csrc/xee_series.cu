@@ -10,7 +10,7 @@
 //   dynamical RHS       src/old-diagnose/diagnose.f90:350-354 (rhoC_C), 359-367 (m^2, intended maths), 412-436
 //   solve               elliptic_tools.f90:93-265, Chebyshev weights per solve (one spectral radius per operator)
 //   u, w, integrals     old-diagnose/diagnose.f90:915-941, 1117-1127, 1029-1113
-// Deviations from the legacy driver's latent bugs are those listed in oracle/xee_oracle.hpp.
+// Deviations from the legacy driver's latent bugs are listed in DESIGN.md section 3.
 #include "xee_map_kernels.cuh"
 
 namespace xee {
@@ -215,7 +215,10 @@ struct Series : SeriesBase {
     series_bc_kernel<T><<<gO, 128, 0, s>>>(snaps, psi, ra, nr, nz); XEE_LAUNCH_OK();
     xee_solve_params prm = *prm_in;
     if (d.r1_rel_rms_f > 0) {
-      rms_interior_kernel<T><<<nb, 256, 0, s>>>(f, nr, nz, (T)d.r1_rel_rms_f, r1v); XEE_LAUNCH_OK();
+      // tolerance relative to the INITIAL residual L psi0 - f: with the pumping boundary condition the boundary data,
+      // not f, set the scale of the problem (u is free scratch here)
+      if (pl->apply(psi, u, s)) return 1;
+      rms_diff_interior_kernel<T><<<nb, 256, 0, s>>>(u, f, nr, nz, (T)d.r1_rel_rms_f, r1v); XEE_LAUNCH_OK();
       prm.r1 = 1.0; prm.r1_per_solve = r1v;
     }
     std::vector<int> iters(nb), err(nb);

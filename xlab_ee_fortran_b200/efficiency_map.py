@@ -25,7 +25,7 @@ class _MapDesc(C.Structure):
 
 def _prm(p: SolveParams):
     return _SolveParams(p.max_iter, p.check_step, p.converge_time, p.lost_rate, p.r1, p.r2, p.alpha, None,
-                        p.rho_jacobi, int(p.detect_explode), p.sync_every)
+                        p.rho_jacobi, int(p.detect_explode), p.sync_every, p.stall_checks)
 
 
 class EfficiencyMap:

@@ -25,7 +25,7 @@ class _PlanDesc(C.Structure):
 class _SolveParams(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("check_step", C.c_int), ("converge_time", C.c_int), ("lost_rate", C.c_int),
                 ("r1", C.c_double), ("r2", C.c_double), ("alpha", C.c_double), ("r1_per_solve", C.c_void_p),
-                ("rho_jacobi", C.c_double), ("detect_explode", C.c_int), ("sync_every", C.c_int)]
+                ("rho_jacobi", C.c_double), ("detect_explode", C.c_int), ("sync_every", C.c_int), ("stall_checks", C.c_int)]
 
 
 @dataclass
@@ -42,6 +42,7 @@ class SolveParams:
     rho_jacobi: float = 0.0
     detect_explode: bool = False
     sync_every: int = 1
+    stall_checks: int = 0           # >0: stop with err bit 4 when the residual stops improving (not in the reference)
 
 
 def _torch():
@@ -112,7 +113,7 @@ class Plan:
     # ---- solves
     def _prm(self, p: SolveParams):
         q = _SolveParams(p.max_iter, p.check_step, p.converge_time, p.lost_rate, p.r1, p.r2, p.alpha, None,
-                         p.rho_jacobi, int(p.detect_explode), p.sync_every)
+                         p.rho_jacobi, int(p.detect_explode), p.sync_every, p.stall_checks)
         if p.r1_per_solve is not None:
             q.r1_per_solve = self._chk(p.r1_per_solve, (self.nbatch,)).value
         return q
