@@ -216,9 +216,9 @@ struct Series : SeriesBase {
     xee_solve_params prm = *prm_in;
     if (d.r1_rel_rms_f > 0) {
       // tolerance relative to the INITIAL residual L psi0 - f: with the pumping boundary condition the boundary data,
-      // not f, set the scale of the problem (u is free scratch here)
-      if (pl->apply(psi, u, s)) return 1;
-      rms_diff_interior_kernel<T><<<nb, 256, 0, s>>>(u, f, nr, nz, (T)d.r1_rel_rms_f, r1v); XEE_LAUNCH_OK();
+      // not f, set the scale of the problem (the plan's second ping-pong buffer is free scratch before the solve)
+      if (pl->apply(psi, pl->x1, s)) return 1;
+      rms_diff_interior_kernel<T><<<nb, 256, 0, s>>>(pl->x1, f, nr, nz, (T)d.r1_rel_rms_f, r1v); XEE_LAUNCH_OK();
       prm.r1 = 1.0; prm.r1_per_solve = r1v;
     }
     std::vector<int> iters(nb), err(nb);
