@@ -374,3 +374,37 @@ def test_chebyshev_with_one_operator_per_solve():
         assert ref["err"] == 0 and rel_l2(got[k], ref["dat"]) < 1e-8
         assert out["iters"][k] * 4 < ref["max_iter"]
     print("per-solve chebyshev sweeps", out["iters"])
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shape,nb", [((200, 200), 1), ((512, 256), 1), ((140, 70), 2), ((67, 35), 1), ((3, 3), 1), ((700, 5), 1)])
+def test_resident_solver_matches_direct_kernel_bitwise(name, shape, nb):
+    """v3 (whole solve in one cooperative launch, kernel=3) against v1 (kernel=1): identical sweep counts, residuals
+    and bit-identical fields, for a stop decided by r1 and for max_iter, STRICT Jacobi and FAST Chebyshev."""
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = shape
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=7 * nx + nb)
+    coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    F = np.stack([f * dt(k + 1) for k in range(nb)]); P = np.stack([x0 * dt(1 + 0.25 * k) for k in range(nb)])
+    rms_f = float(np.sqrt((F[0].astype(np.float64) ** 2).mean()))
+    cases = [("strict", "jacobi", X.SolveParams(max_iter=237, check_step=10, converge_time=3, r1=1e-30, r2=1.0, alpha=0.9)),
+             ("strict", "jacobi", X.SolveParams(max_iter=100000, check_step=20, converge_time=2, lost_rate=3, r1=(3e-2 if name == "f32" else 1e-3) * rms_f, r2=0.0, alpha=1.0)),
+             ("fast", "chebyshev", X.SolveParams(max_iter=5000, check_step=10, converge_time=2, r1=(1e-1 if name == "f32" else 1e-4) * rms_f, r2=0.0, rho_jacobi=0.98))]
+    for arith, method, prm in cases:
+        res = {}
+        for kern in (1, 3):
+            plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=True, arith=arith, method=method, kernel=kern)
+            plan.set_coe_aos(coe)
+            psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+            out = plan.solve(psi, ft, prm)
+            res[kern] = (psi.cpu().numpy(), out)
+            plan.close()
+        assert list(res[1][1]["iters"]) == list(res[3][1]["iters"]), (arith, method)
+        assert list(res[1][1]["err"]) == list(res[3][1]["err"])
+        assert np.array_equal(res[1][0], res[3][0]), (arith, method)
+        assert np.allclose(res[1][1]["r1"], res[3][1]["r1"], rtol=1e-12 if name == "f64" else 1e-5)
+    # the first case also against the oracle, bit for bit
+    rb = O.solve_batch(237, 10, 3, 5, 1e-30, 1.0, 0.9, P, coe, F, threads=2)
+    plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=True, arith="strict", kernel=3); plan.set_coe_aos(coe)
+    psi = torch.from_numpy(P).cuda(); plan.solve(psi, torch.from_numpy(F).cuda(), cases[0][2])
+    assert np.array_equal(psi.cpu().numpy(), rb["dat"])

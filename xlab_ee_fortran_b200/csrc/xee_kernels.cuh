@@ -150,6 +150,11 @@ __host__ __device__ inline double cheb_omega(int k, double rho) {
   return (2.0 / rho) * q * (1.0 + q2k) / (1.0 + q2k * q * q);
 }
 
+// The sequence omega_k converges to 2/(1+sqrt(1-rho^2)); beyond kChebClamp sweeps it is constant to double precision
+// for any rho <= 1 - 1e-7.  Every kernel variant uses omega_{min(k, kChebClamp)} so that they stay bit-identical.
+constexpr int kChebClamp = 8192;
+inline double cheb_omega_host(int k, double rho) { return cheb_omega(k < kChebClamp ? k : kChebClamp, rho); }
+
 constexpr int kDirBX = 64, kDirBY = 4;
 
 // v1 "direct" sweep: one thread per grid point, the block walks `spb` solves with the nine

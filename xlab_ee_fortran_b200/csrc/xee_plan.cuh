@@ -14,6 +14,7 @@
 
 #include "xee_kernels.cuh"
 #include "xee_sweep_tma.cuh"
+#include "xee_resident.cuh"
 
 namespace xee {
 
@@ -242,7 +243,8 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev); }
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+      pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
       pool_free(st.done); pool_free(st.iters); pool_free(st.ccnt); pool_free(st.lcnt); pool_free(st.errb);
@@ -383,6 +385,43 @@ struct Plan : PlanBase {
 
   // Power iteration on the Jacobi iteration matrix G = I - D^-1 L (homogeneous problem, zero
   // boundary): rho ~ ||G^{k+1} e|| / ||G^k e||.  Uses x1 and a scratch batch of size 1.
+  // v3 resident solver (one cooperative launch per solve_elliptic call); see xee_resident.cuh
+  int res_G = 0, res_P = 0;          // strips per solve, points per thread (0 = does not fit)
+  T *res_final = nullptr, *res_prev = nullptr, *res_halo = nullptr;
+  int* res_ints = nullptr;           // flags[nb*G] | check_cnt[nb] | abort[1]
+  T* res_omega = nullptr;            // Chebyshev weights omega_1..omega_kChebClamp
+  double* res_partial = nullptr;
+  bool resident_fits() {
+    if (res_G) return res_P > 0;
+    const int rows = d.ny - 2, w = d.nx - 2;
+    int G = std::min(num_sms / std::max(1, d.nbatch), rows);
+    if (G < 1) { res_G = 1; res_P = 0; return false; }
+    const int rows_max = (rows + G - 1) / G;
+    const long long pts = (long long)rows_max * w;
+    res_G = G;
+    res_P = pts <= res::NT ? 1 : pts <= 2 * res::NT ? 2 : pts <= 3 * res::NT ? 3 : 0;
+    if ((size_t)(rows_max + 2) * d.nx * sizeof(T) > 200 * 1024) res_P = 0;
+    return res_P > 0;
+  }
+  template <int ARITH, int MODE, int P>
+  int launch_resident(res::ResArgs<T>& ra, cudaStream_t s) {
+    auto kern = res::solve_resident_kernel<T, ARITH, MODE, P>;
+    const int rows_max = (d.ny - 2 + res_G - 1) / res_G;
+    const size_t smem = (size_t)(rows_max + 2) * d.nx * sizeof(T);
+    XEE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    XEE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, res::NT, smem));
+    if ((long long)per_sm * num_sms < (long long)res_G * d.nbatch) return fail("xee: resident solver does not fit on the device (co-residency)");
+    void* params[] = {(void*)&ra};
+    XEE_CHECK(cudaLaunchCooperativeKernel((void*)kern, dim3(res_G, d.nbatch), dim3(res::NT), params, smem, s));
+    XEE_LAUNCH_OK();
+    return 0;
+  }
+  template <int ARITH, int MODE>
+  int launch_resident_p(res::ResArgs<T>& ra, cudaStream_t s) {
+    return res_P == 1 ? launch_resident<ARITH, MODE, 1>(ra, s) : res_P == 2 ? launch_resident<ARITH, MODE, 2>(ra, s) : launch_resident<ARITH, MODE, 3>(ra, s);
+  }
+  int solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int check_step, int converge_time, int lost_rate, int mode, cudaStream_t s);
   int estimate_rho(cudaStream_t s);
   // Make the Chebyshev parameters of this call available: explicit value, cached estimate, or a fresh estimate.
   int prepare_cheb(double rho_given, cudaStream_t s) {
@@ -409,7 +448,7 @@ struct Plan : PlanBase {
     for (int cnt = 1; cnt <= nsw; ++cnt) {
       const T* src = (cnt & 1) ? x0 : x1;
       T* dst = (cnt & 1) ? x1 : x0;
-      const double om = mode == MODE_CHEBYSHEV ? cheb_omega(cnt, cheb_rho) : 1.0;
+      const double om = mode == MODE_CHEBYSHEV ? cheb_omega_host(cnt, cheb_rho) : 1.0;
       SweepArgs<T> a = args(src, dst, (const T*)f, (T)alpha, (T)om, nullptr);
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, rms && cnt == nsw, s)) return 1;
@@ -540,6 +579,56 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
 }
 
 template <class T>
+int Plan<T>::solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int check_step, int converge_time,
+                            int lost_rate, int mode, cudaStream_t s) {
+  const int nb = d.nbatch, G = res_G;
+  const size_t fbytes = sizeof(T) * nn * nb;
+  if (!res_final) {
+    XEE_CHECK(pool_alloc(&res_final, fbytes)); XEE_CHECK(pool_alloc(&res_prev, fbytes));
+    XEE_CHECK(pool_alloc(&res_halo, sizeof(T) * (size_t)nb * 2 * G * 2 * d.nx));
+    XEE_CHECK(pool_alloc(&res_ints, sizeof(int) * ((size_t)nb * G + nb + 1)));
+    XEE_CHECK(pool_alloc(&res_partial, sizeof(double) * (size_t)nb * 2 * G));
+  }
+  XEE_CHECK(cudaMemsetAsync(res_ints, 0, sizeof(int) * ((size_t)nb * G + nb + 1), s));
+  XEE_CHECK(cudaMemcpyAsync(res_final, x0, fbytes, cudaMemcpyDeviceToDevice, s));   // boundary values in both outputs
+  XEE_CHECK(cudaMemcpyAsync(res_prev, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+  res::ResArgs<T> ra{};
+  ra.psi0 = x0; ra.f = fd; ra.coe = coe;
+  ra.coe_set_stride = d.shared_coe ? 0 : (long long)kPlanes * nn; ra.field_stride = (long long)nn;
+  ra.out_final = res_final; ra.out_prev = res_prev; ra.halo = res_halo;
+  ra.flags = res_ints; ra.check_cnt = res_ints + (size_t)nb * G; ra.abort_flag = res_ints + (size_t)nb * G + nb;
+  ra.partial = res_partial;
+  ra.nx = d.nx; ra.ny = d.ny; ra.G = G;
+  ra.max_iter = prm->max_iter; ra.check_step = check_step; ra.converge_time = converge_time; ra.lost_rate = lost_rate;
+  ra.alpha = (T)prm->alpha; ra.rho = cheb_rho;
+  if (mode == MODE_CHEBYSHEV) {   // host-computed weights, the same values the per-launch kernels receive
+    if (!res_omega) XEE_CHECK(pool_alloc(&res_omega, sizeof(T) * kChebClamp));
+    std::vector<T> tab(kChebClamp);
+    for (int k = 1; k <= kChebClamp; ++k) tab[k - 1] = (T)cheb_omega_host(k, cheb_rho);
+    XEE_CHECK(cudaMemcpyAsync(res_omega, tab.data(), sizeof(T) * kChebClamp, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaStreamSynchronize(s));
+  }
+  ra.omega_tab = res_omega;
+  ra.r1 = st.r1; ra.r2 = st.r2; ra.detect_explode = prm->detect_explode; ra.stall_checks = prm->stall_checks;
+  ra.iters = st.iters; ra.errb = st.errb; ra.err_now = st.err_now; ra.ratio = st.ratio;
+  ra.trace_err = st.trace_err; ra.trace_ratio = st.trace_ratio; ra.trace_cap = st.trace_cap;
+  const bool strict = d.arith == XEE_ARITH_STRICT;
+  int rc;
+  if (mode == MODE_JACOBI) rc = strict ? launch_resident_p<XEE_ARITH_STRICT, MODE_JACOBI>(ra, s) : launch_resident_p<XEE_ARITH_FAST, MODE_JACOBI>(ra, s);
+  else rc = strict ? launch_resident_p<XEE_ARITH_STRICT, MODE_CHEBYSHEV>(ra, s) : launch_resident_p<XEE_ARITH_FAST, MODE_CHEBYSHEV>(ra, s);
+  if (rc) return rc;
+  // dat <- last iterate; the other buffer as the reference leaves `workspace` (penultimate iterate when the
+  // sweep count is even, a copy of the result when it is odd: elliptic_tools.f90:259-264)
+  XEE_CHECK(cudaMemcpyAsync(x0, res_final, fbytes, cudaMemcpyDeviceToDevice, s));
+  std::vector<int> hi(nb);
+  XEE_CHECK(cudaMemcpyAsync(hi.data(), st.iters, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+  XEE_CHECK(cudaStreamSynchronize(s));
+  for (int n = 0; n < nb; ++n)
+    XEE_CHECK(cudaMemcpyAsync(x1 + (size_t)n * nn, ((hi[n] & 1) ? res_final : res_prev) + (size_t)n * nn, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+template <class T>
 int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* iters, double* r1o, double* r2o,
                    int* err, cudaStream_t s, bool host_io, void* workspace_host, int debug) {
   const int nb = d.nbatch;
@@ -562,6 +651,46 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   }
   init_state_kernel<T><<<(nb + 127) / 128, 128, 0, s>>>(st, nb, (T)prm->r1, (T)prm->r2, (const T*)prm->r1_per_solve);
   XEE_LAUNCH_OK();
+  // v3: the whole loop in one cooperative launch (single / few solves that fit on the chip)
+  int want_kernel = d.kernel > 0 ? d.kernel : env_int("XEE_KERNEL", 0);
+  const bool resident_ok = (d.shared_coe || nb == 1) && max_iter >= 1 && resident_fits();
+  if (want_kernel == 3 && !resident_ok) return fail("xee: kernel=3 (resident) needs a problem that fits: nbatch*strips <= SMs, <= 1536 points per strip");
+  if (want_kernel == 3 || (want_kernel == 0 && resident_ok && nb <= 2)) {
+    cudaEvent_t e0 = next_event(), e1 = next_event();
+    XEE_CHECK(cudaEventRecord(e0, s));
+    if (solve_resident(x0, fd, prm, check_step, converge_time, lost_rate, mode, s)) return 1;
+    XEE_CHECK(cudaEventRecord(e1, s));
+    std::vector<int> hi(nb), he(nb);
+    std::vector<T> h1(nb), h2(nb);
+    XEE_CHECK(cudaMemcpyAsync(hi.data(), st.iters, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    XEE_CHECK(cudaMemcpyAsync(he.data(), st.errb, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    XEE_CHECK(cudaMemcpyAsync(h1.data(), st.err_now, sizeof(T) * nb, cudaMemcpyDeviceToHost, s));
+    XEE_CHECK(cudaMemcpyAsync(h2.data(), st.ratio, sizeof(T) * nb, cudaMemcpyDeviceToHost, s));
+    if (host_io) {
+      XEE_CHECK(cudaMemcpyAsync(psi, x0, fbytes, cudaMemcpyDeviceToHost, s));
+      if (workspace_host) XEE_CHECK(cudaMemcpyAsync(workspace_host, x1, fbytes, cudaMemcpyDeviceToHost, s));
+    }
+    XEE_CHECK(cudaStreamSynchronize(s));
+    harvest_events();
+    for (int n = 0; n < nb; ++n) {
+      if (he[n] & 0x100) return fail("xee: resident solver watchdog tripped (a CTA waited too long for its neighbour)");
+      sweep_launches += hi[n];
+      if (iters) iters[n] = hi[n];
+      if (err) err[n] = he[n];
+      if (r1o) r1o[n] = (double)h1[n];
+      if (r2o) r2o[n] = (double)h2[n];
+    }
+    if (debug == 2) {
+      const int nchk = std::min(hi[0] / check_step, st.trace_cap);
+      std::vector<T> te(nchk), tr(nchk);
+      if (nchk > 0) {
+        XEE_CHECK(cudaMemcpy(te.data(), st.trace_err, sizeof(T) * nchk, cudaMemcpyDeviceToHost));
+        XEE_CHECK(cudaMemcpy(tr.data(), st.trace_ratio, sizeof(T) * nchk, cudaMemcpyDeviceToHost));
+      }
+      for (int q = 0; q < nchk; ++q) printf("Iter: %8d, err_now: %12.3E, ratio: %12.3E\n", (q + 1) * check_step, (double)te[q], (double)tr[q]);
+    }
+    return 0;
+  }
   // workspace = dat: both ping-pong buffers start as boundary + first guess (:166-171)
   XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
   if (prepare_maps(x0, x1, fd, nb)) return 1;
@@ -581,7 +710,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
       const T* src = (cnt & 1) ? x0 : x1;   // sweep cnt reads the buffer written by sweep cnt-1
       T* dst = (cnt & 1) ? x1 : x0;
       const bool check = (cnt % check_step) == 0;                                // :179-183
-      const double om = mode == MODE_CHEBYSHEV ? cheb_omega(cnt, cheb_rho) : 1.0;
+      const double om = mode == MODE_CHEBYSHEV ? cheb_omega_host(cnt, cheb_rho) : 1.0;
       SweepArgs<T> a = args(src, dst, fd, (T)prm->alpha, (T)om, st.done);
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, check, s)) return 1;
