@@ -399,27 +399,27 @@ struct Plan : PlanBase {
     const int rows_max = (rows + G - 1) / G;
     const long long pts = (long long)rows_max * w;
     res_G = G;
-    res_P = pts <= res::NT ? 1 : pts <= 2 * res::NT ? 2 : pts <= 3 * res::NT ? 3 : 0;
+    res_P = pts <= 512 ? 1 : pts <= 2 * 512 ? 2 : pts <= 3 * 512 ? 3 : 0;       // 512 threads x P points (1024 x 1 measured slower)
     if ((size_t)(rows_max + 2) * d.nx * sizeof(T) > 200 * 1024) res_P = 0;
     return res_P > 0;
   }
-  template <int ARITH, int MODE, int P>
+  template <int ARITH, int MODE, int P, int NT>
   int launch_resident(res::ResArgs<T>& ra, cudaStream_t s) {
-    auto kern = res::solve_resident_kernel<T, ARITH, MODE, P>;
+    auto kern = res::solve_resident_kernel<T, ARITH, MODE, P, NT>;
     const int rows_max = (d.ny - 2 + res_G - 1) / res_G;
     const size_t smem = (size_t)(rows_max + 2) * d.nx * sizeof(T);
     XEE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    XEE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, res::NT, smem));
+    XEE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if ((long long)per_sm * num_sms < (long long)res_G * d.nbatch) return fail("xee: resident solver does not fit on the device (co-residency)");
     void* params[] = {(void*)&ra};
-    XEE_CHECK(cudaLaunchCooperativeKernel((void*)kern, dim3(res_G, d.nbatch), dim3(res::NT), params, smem, s));
+    XEE_CHECK(cudaLaunchCooperativeKernel((void*)kern, dim3(res_G, d.nbatch), dim3(NT), params, smem, s));
     XEE_LAUNCH_OK();
     return 0;
   }
   template <int ARITH, int MODE>
   int launch_resident_p(res::ResArgs<T>& ra, cudaStream_t s) {
-    return res_P == 1 ? launch_resident<ARITH, MODE, 1>(ra, s) : res_P == 2 ? launch_resident<ARITH, MODE, 2>(ra, s) : launch_resident<ARITH, MODE, 3>(ra, s);
+    return res_P == 1 ? launch_resident<ARITH, MODE, 1, 512>(ra, s) : res_P == 2 ? launch_resident<ARITH, MODE, 2, 512>(ra, s) : launch_resident<ARITH, MODE, 3, 512>(ra, s);
   }
   int solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int check_step, int converge_time, int lost_rate, int mode, cudaStream_t s);
   int estimate_rho(cudaStream_t s);
@@ -586,17 +586,17 @@ int Plan<T>::solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int
   if (!res_final) {
     XEE_CHECK(pool_alloc(&res_final, fbytes)); XEE_CHECK(pool_alloc(&res_prev, fbytes));
     XEE_CHECK(pool_alloc(&res_halo, sizeof(T) * (size_t)nb * 2 * G * 2 * d.nx));
-    XEE_CHECK(pool_alloc(&res_ints, sizeof(int) * ((size_t)nb * G + nb + 1)));
+    XEE_CHECK(pool_alloc(&res_ints, sizeof(int) * ((size_t)nb * G * res::FLAG_PAD + 64 * nb + 64)));
     XEE_CHECK(pool_alloc(&res_partial, sizeof(double) * (size_t)nb * 2 * G));
   }
-  XEE_CHECK(cudaMemsetAsync(res_ints, 0, sizeof(int) * ((size_t)nb * G + nb + 1), s));
+  XEE_CHECK(cudaMemsetAsync(res_ints, 0, sizeof(int) * ((size_t)nb * G * res::FLAG_PAD + 64 * nb + 64), s));
   XEE_CHECK(cudaMemcpyAsync(res_final, x0, fbytes, cudaMemcpyDeviceToDevice, s));   // boundary values in both outputs
   XEE_CHECK(cudaMemcpyAsync(res_prev, x0, fbytes, cudaMemcpyDeviceToDevice, s));
   res::ResArgs<T> ra{};
   ra.psi0 = x0; ra.f = fd; ra.coe = coe;
   ra.coe_set_stride = d.shared_coe ? 0 : (long long)kPlanes * nn; ra.field_stride = (long long)nn;
   ra.out_final = res_final; ra.out_prev = res_prev; ra.halo = res_halo;
-  ra.flags = res_ints; ra.check_cnt = res_ints + (size_t)nb * G; ra.abort_flag = res_ints + (size_t)nb * G + nb;
+  ra.flags = res_ints; ra.check_cnt = res_ints + (size_t)nb * G * res::FLAG_PAD; ra.abort_flag = ra.check_cnt + 64 * nb;
   ra.partial = res_partial;
   ra.nx = d.nx; ra.ny = d.ny; ra.G = G;
   ra.max_iter = prm->max_iter; ra.check_step = check_step; ra.converge_time = converge_time; ra.lost_rate = lost_rate;
@@ -609,6 +609,7 @@ int Plan<T>::solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int
     XEE_CHECK(cudaStreamSynchronize(s));
   }
   ra.omega_tab = res_omega;
+  ra.dbg = env_int("XEE_RES_DEBUG", 0);
   ra.r1 = st.r1; ra.r2 = st.r2; ra.detect_explode = prm->detect_explode; ra.stall_checks = prm->stall_checks;
   ra.iters = st.iters; ra.errb = st.errb; ra.err_now = st.err_now; ra.ratio = st.ratio;
   ra.trace_err = st.trace_err; ra.trace_ratio = st.trace_ratio; ra.trace_cap = st.trace_cap;

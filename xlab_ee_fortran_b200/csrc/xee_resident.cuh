@@ -20,14 +20,21 @@
 namespace xee {
 namespace res {
 
-constexpr int NT = 512;               // threads per CTA
-constexpr long long SPIN_LIMIT = 1LL << 26;   // watchdog: ~ seconds of spinning, then the solve aborts
+constexpr int NT_MAX = 1024;          // threads per CTA: 1024 x 1 point, or 512 x 2..3 points per thread
+constexpr int FLAG_PAD = 32;          // ints per flag: one 128-byte line per CTA, so pollers never share a line with a writer
+constexpr long long SPIN_LIMIT = 1LL << 22;   // watchdog: ~1-2 s of spinning on one flag, then the solve aborts
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -41,14 +48,15 @@ struct ResArgs {
   T* out_final;         // [nb][ny][nx] last iterate
   T* out_prev;          // [nb][ny][nx] penultimate iterate (what the reference leaves in the other buffer)
   T* halo;              // [nb][2][G][2][nx] exchange rows
-  int* flags;           // [nb][G] sweeps completed by each CTA
+  int* flags;           // [nb][G][FLAG_PAD] sweeps completed by each CTA (word 0 of its own 128-byte line)
   double* partial;      // [nb][2][G] sum of r^2 per CTA, double-buffered by check parity
-  int* check_cnt;       // [nb] monotonic arrival counter for checks
+  int* check_cnt;       // [nb][64] monotonic arrival counter for checks (padded)
   int* abort_flag;      // [1] watchdog tripped
   int nx, ny, G;
   int max_iter, check_step, converge_time, lost_rate;
   T alpha; double rho;  // rho: Jacobi spectral radius (Chebyshev)
   const T* omega_tab;   // [kChebClamp] host-computed Chebyshev weights
+  int dbg;              // timing experiments only (XEE_RES_DEBUG): 1 skip neighbour wait, 2 skip halo pull, 4 skip release
   const T* r1; const T* r2;   // [nb] thresholds (HUGE when disabled)
   int detect_explode, stall_checks;
   // results
@@ -63,7 +71,7 @@ __host__ __device__ inline void strip_rows(int g, int G, int ny, int& r0, int& r
   r1 = r0 + base + (g < rem ? 1 : 0);
 }
 
-template <class T, int ARITH, int MODE, int P>
+template <class T, int ARITH, int MODE, int P, int NT>
 __global__ void __launch_bounds__(NT, 1) solve_resident_kernel(const ResArgs<T> a) {
   using R = Rn<T>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,6 +79,8 @@ __global__ void __launch_bounds__(NT, 1) solve_resident_kernel(const ResArgs<T> 
   __shared__ double red[NT / 32];
   __shared__ double sh_tot;
   __shared__ T sh_omega;
+  __shared__ int sh_abort;
+  if (threadIdx.x == 0) sh_abort = 0;
 
   const int g = blockIdx.x, n = blockIdx.y, G = a.G, tid = threadIdx.x;
   const int nx = a.nx, ny = a.ny, w = nx - 2;
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(NT, 1) solve_resident_kernel(const ResArgs<T> 
   const T* fn = a.f + (size_t)n * nn;
   const T* cn = a.coe + (size_t)n * a.coe_set_stride;
   T* halo = a.halo + (size_t)n * 2 * G * 2 * nx;
-  int* flags = a.flags + (size_t)n * G;
+  int* flags = a.flags + (size_t)n * G * FLAG_PAD;
   double* partial = a.partial + (size_t)n * 2 * G;
 
   // ---- load the strip (+ halo rows, + boundary columns) and the per-point operator
@@ -150,45 +160,48 @@ __global__ void __launch_bounds__(NT, 1) solve_resident_kernel(const ResArgs<T> 
       const double tot = block_sum(rr, red, tid, NT / 32);
       if (tid == 0) { __stcg(&partial[(size_t)(check_idx & 1) * G + g], tot); }
     }
-    __threadfence();
-    __syncthreads();                                // strip updated, exchange rows and partial written
+    __syncthreads();                                // strip updated; exchange rows and partial issued by the CTA
     if (tid == 0) {
-      st_release(&flags[g], cnt);
-      if (check) atomicAdd(&a.check_cnt[n], 1);
+      // release (cumulative over the CTA's writes ordered before it by the barrier): publish sweep `cnt`
+      if (!(a.dbg & 4)) st_release(&flags[(size_t)g * FLAG_PAD], cnt);
+      if (check) atomicAdd(&a.check_cnt[(size_t)n * 64], 1);
     }
-    // ---- wait for the two neighbours to have finished sweep cnt, then pull their rows into the halo rows
+    // ---- wait for the two neighbours to have finished sweep cnt, then pull their rows into the halo rows.
+    // Only the two polling threads ever touch the flags; the shared abort word is read only while spinning long.
     if (tid < 2) {
       const int nb = (tid == 0) ? g - 1 : g + 1;
-      if (nb >= 0 && nb < G) {
+      if (nb >= 0 && nb < G && !(a.dbg & 1)) {
         long long spins = 0;
-        while (ld_acquire(&flags[nb]) < cnt) {
-          if (++spins > SPIN_LIMIT || ld_acquire(a.abort_flag)) { atomicExch(a.abort_flag, 1); break; }
+        while (ld_acquire(&flags[(size_t)nb * FLAG_PAD]) < cnt) {
+          if ((++spins & 0xfff) == 0 && (spins > SPIN_LIMIT || ld_acquire(a.abort_flag))) { atomicExch(a.abort_flag, 1); sh_abort = 1; break; }
         }
       }
     }
     __syncthreads();
-    if (ld_acquire(a.abort_flag)) { aborted = true; break; }
-    if (g > 0) {
-      const T* src = halo + ((size_t)par * G + (g - 1)) * 2 * nx + nx;   // last row of CTA g-1
-      for (int i = 1 + tid; i <= w; i += NT) sp[i] = __ldcg(src + i);
-    }
-    if (g < G - 1) {
-      const T* src = halo + ((size_t)par * G + (g + 1)) * 2 * nx;        // first row of CTA g+1
-      for (int i = 1 + tid; i <= w; i += NT) sp[(size_t)(rows + 1) * nx + i] = __ldcg(src + i);
+    if (sh_abort) { aborted = true; break; }
+    if (!(a.dbg & 2)) {   // both neighbour rows: issue every load before the first shared-memory store
+      const T* lo = halo + ((size_t)par * G + (g > 0 ? g - 1 : 0)) * 2 * nx + nx;       // last row of CTA g-1
+      const T* hi = halo + ((size_t)par * G + (g < G - 1 ? g + 1 : g)) * 2 * nx;        // first row of CTA g+1
+      for (int i = 1 + tid; i <= w; i += NT) {
+        const T vlo = (g > 0) ? __ldcg(lo + i) : sp[i];
+        const T vhi = (g < G - 1) ? __ldcg(hi + i) : sp[(size_t)(rows + 1) * nx + i];
+        sp[i] = vlo; sp[(size_t)(rows + 1) * nx + i] = vhi;
+      }
     }
     // ---- stop rule (elliptic_tools.f90:192-234), evaluated redundantly by every CTA on identical data
     if (check) {
       if (tid == 0) {
         long long spins = 0;
         const int want = (check_idx + 1) * G;
-        while (ld_acquire(&a.check_cnt[n]) < want) {
-          if (++spins > SPIN_LIMIT || ld_acquire(a.abort_flag)) { atomicExch(a.abort_flag, 1); break; }
+        while (ld_acquire(&a.check_cnt[(size_t)n * 64]) < want) {
+          if ((++spins & 0xfff) == 0 && (spins > SPIN_LIMIT || ld_acquire(a.abort_flag))) { atomicExch(a.abort_flag, 1); sh_abort = 1; break; }
         }
         double t = 0.0;
         for (int q = 0; q < G; ++q) t += __ldcg(&partial[(size_t)(check_idx & 1) * G + q]);
         sh_tot = t;
       }
       __syncthreads();
+      if (sh_abort) { aborted = true; break; }
       const double tot = sh_tot;
       err_now = R::sqrt(R::div((T)tot, (T)((nx - 2) * (ny - 2))));                 // :199
       ratio = R::div(R::sub(err_before, err_now), err_before);                     // :201
