@@ -67,6 +67,19 @@ void xee_solve_elliptic_f64(int* max_iter, const int* check_step, const int* con
                             const double* coe, const double* f, double* workspace, const int* nx, const int* ny,
                             int* err, const int* debug);
 
+/* LEGACY signature: solve_elliptic(max_iter, strategy, strategy_r, alpha, dat, coe, f, workspace, nx, ny, err, debug)
+ * src/old-diagnose/xtt-lib/elliptic_tools.f90:93-300, called nine times by src/old-diagnose/diagnose.f90:449-714.
+ * strategy 1: stop when the RMS residual < strategy_r at a check (every 100 sweeps); strategy 2: stop when the relative
+ * change of the residual stays < strategy_r for 10 checks (hysteresis 5).  On return strategy = sweeps used,
+ * strategy_r = last residual.  Strategies 3/4 (max-abs residual) are not provided: err = 2^8 and no work is done.
+ * As in the legacy code, max_iter is only honoured on check sweeps (multiples of 100). */
+void xee_solve_elliptic_old_f32(const int* max_iter, int* strategy, float* strategy_r, const float* alpha, float* dat,
+                                const float* coe, const float* f, float* workspace, const int* nx, const int* ny,
+                                int* err, const int* debug);
+void xee_solve_elliptic_old_f64(const int* max_iter, int* strategy, double* strategy_r, const double* alpha, double* dat,
+                                const double* coe, const double* f, double* workspace, const int* nx, const int* ny,
+                                int* err, const int* debug);
+
 /* judge_error(err)                                     elliptic_tools.f90:333-358 */
 void xee_judge_error(const int* err);
 

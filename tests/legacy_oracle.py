@@ -1,0 +1,93 @@
+"""Oracle-side composition of the legacy TENDENCY decomposition (src/old-diagnose/diagnose.f90:238-841) in numpy
+(float64) on top of the C++ oracle's solver, with the same stated deviations [D1]-[D6] as
+xlab_ee_fortran_b200/csrc/xee_old_diagnose.cpp.  Arrays are [j][i] (Fortran f(i,j) -> f[j-1, i-1])."""
+import numpy as np
+
+from oracle import numpy_ref as N
+from oracle import oracle as O
+
+
+def old_solve(strategy, strategy_r, max_iter, alpha, dat, coe, f):
+    """Legacy 12-argument solve_elliptic (old-diagnose/xtt-lib/elliptic_tools.f90:93-300), strategies 1 and 2."""
+    eff = (max_iter // 100) * 100
+    if strategy == 1:
+        r = O.solve_elliptic(eff, 100, 1, 5, strategy_r, 0.0, alpha, dat, coe, f)
+    else:
+        r = O.solve_elliptic(eff, 100, 10, 5, 0.0, strategy_r, alpha, dat, coe, f)
+    return r["dat"], r["max_iter"], r["r1"]
+
+
+def decompose(A, B, C, Q, F, Lr, Lz, testing_dt, rpsi_set, rchi_set, baro=2, rchi_bc=None, rpsi_bc=None, tendency=True):
+    """rpsi_set / rchi_set = (strategy, strategy_r, max_iter, alpha).  Returns dict of sums and fields."""
+    dt = np.float64
+    nz, nr = A.shape
+    d = O.Domain(Lr, Lz, nr, nz, 0, 0)
+    g = O.geometry(d, dt)
+    k = N.constants(dt)
+    g0, th0, Cp = k["g0"], k["theta0"], k["Cp"]
+    ra, za, rho, ex = g["ra"], g["za"], g["rho"], g["exner"]
+    A, B, C, Q, F = (np.asarray(x, dt) for x in (A, B, C, Q, F))
+    intB = lambda w: O.integrate_weight_B(np.ascontiguousarray(w), d)
+    sum_Q = intB(Q)
+    a, b_basic_s, c = O.build_abc(A, B, C, d)
+    rA, rBC, rBB, rCC = O.stagger_averages(A, B, C, d)
+    b_basic = rBB.copy()
+    m2 = O.angular_momentum_sq(rCC, d)
+    J, rhs_thm = O.rhs_thermal(Q, d)
+    rhs_mom = O.rhs_momentum(m2, F, d)
+    out = dict(sum_Q=sum_Q)
+    coe_of = lambda bb: O.cal_coe(a, bb, c, g["dr"], g["dz"], nr, nz)[0]
+    b_anom = np.zeros_like(rBB); sb_anom = np.zeros_like(rBB)
+    if tendency:
+        psi0 = np.zeros((nz, nr)) if rpsi_bc is None else rpsi_bc.astype(dt)
+        rpsi, it, res = old_solve(*rpsi_set[:2], rpsi_set[2], rpsi_set[3], psi0, coe_of(b_basic_s), rhs_thm + rhs_mom)
+        out["rpsi_before"] = rpsi
+        u, w = O.cal_uw(rpsi, d)
+        th = J - th0 / g0 * (rA[:-1] * w[:-1] + rA[1:] * w[1:]) / 2.0 + th0 / g0 * (rBC[:, :-1] * u[:, :-1] + rBC[:, 1:] * u[:, 1:]) / 2.0
+        out["dtheta_dt"] = th.copy(); out["sum_dtheta_dt"] = intB(th)
+        th = th * testing_dt
+        dB = np.zeros_like(th)                                       # d_dr_B2B
+        dB[:, 1:-1] = (th[:, :-2] - th[:, 2:]) / (ra[:-3] - ra[2:-1])[None, :]
+        dB[:, 0] = (th[:, 0] - th[:, 1]) / (ra[0] - ra[1]); dB[:, -1] = (th[:, -2] - th[:, -1]) / (ra[-3] - ra[-2])
+        b_anom = -g0 / th0 * dB
+        rBB = rBB + b_anom
+        dA = np.zeros((nz, nr - 1))                                   # d_dz_B2A on rows 2..nz-2, [D3] 0 elsewhere
+        dA[1:nz - 2] = (th[1:nz - 2] - th[0:nz - 3]) / ((za[2:nz - 1] - za[0:nz - 3]) / 2.0)[:, None]
+        rA = rA.copy(); rA[1:nz - 1] = rA[1:nz - 1] + g0 / th0 * dA[1:nz - 1]
+    rBC = rBC.copy(); rBC[:, 1:-1] = (rBB[:, :-1] + rBB[:, 1:]) / 2.0
+    theta = O.relative_theta(rA * (th0 / g0), rBC * (-th0 / g0), d)
+    out["theta_after"] = theta
+    rs = ((ra[:-1] + ra[1:]) / 2.0)[None, :]; rr = ((rho[:-1] + rho[1:]) / 2.0)[:, None]
+    sb_anom = b_anom / rs / rr
+    f_basic = O.rhs_from_B(b_basic, d); f_anom = O.rhs_from_B(b_anom, d)
+    ops = {}
+    if baro in (0, 2): ops["0"] = coe_of(np.zeros_like(b_basic_s))
+    if baro in (1, 2): ops["B0dB"] = coe_of(b_basic_s + sb_anom)
+    def eta_sum(chi):
+        eta = O.cal_eta(chi, d)
+        return O.cal_sum_Qeta(Q, eta, d)
+    order = []
+    rchi = np.zeros((nz, nr))
+    if rchi_bc is not None:
+        rchi = rchi_bc.astype(dt)
+        for tag in ("0", "B0dB"):
+            if tag in ops: order.append((tag, None, f"{tag}_0"))
+    seq2 = []
+    for rhs, name in ((f_anom, "dB"), (f_basic, "B0")):
+        for tag in ("0", "B0dB"):
+            if tag in ops: seq2.append((tag, rhs, f"{tag}_{name}"))
+    for tag, rhs, name in order:
+        rchi, it, res = old_solve(*rchi_set[:2], rchi_set[2], rchi_set[3], rchi, ops[tag], np.zeros((nz, nr)))
+        out[f"rchi_{name}"] = rchi; out[f"sum_Qeta_{name}"] = eta_sum(rchi)
+    rchi = np.zeros((nz, nr))
+    for tag, rhs, name in seq2:
+        rchi, it, res = old_solve(*rchi_set[:2], rchi_set[2], rchi_set[3], rchi, ops[tag], rhs)
+        out[f"rchi_{name}"] = rchi; out[f"sum_Qeta_{name}"] = eta_sum(rchi)
+    rpsi = np.zeros((nz, nr)) if rpsi_bc is None else rpsi_bc.astype(dt)
+    for tag in ("0", "B0dB"):
+        if tag not in ops: continue
+        rpsi, it, res = old_solve(*rpsi_set[:2], rpsi_set[2], rpsi_set[3], rpsi, ops[tag], rhs_thm + rhs_mom)
+        u, w = O.cal_uw(rpsi, d)
+        out[f"rpsi_after_{tag}"] = rpsi
+        out[f"sum_wtheta_{tag}"] = intB(O.cal_wtheta(w, theta, d)) * g0 / th0
+    return out

@@ -36,19 +36,30 @@ def _stale() -> bool:
 
 
 DIAGNOSE = os.path.join(_PKG, "bin", "xee_diagnose")
+OLD_DIAGNOSE = os.path.join(_PKG, "bin", "xee_old_diagnose")
+
+
+def _build_host_program(src_name: str, exe: str, force: bool) -> str:
+    src = os.path.join(CSRC, src_name)
+    if force or not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe) or os.path.getmtime(SO) > os.path.getmtime(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", src, "-L" + LIBDIR, "-lxee_b200", "-Wl,-rpath," + LIBDIR,
+               "-Wl,-rpath,$ORIGIN/../lib", "-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return exe
 
 
 def build_diagnose(force: bool = False) -> str:
     """Host-only C++ re-host of the reference driver (csrc/xee_diagnose.cpp), linked against libxee_b200.so."""
-    src = os.path.join(CSRC, "xee_diagnose.cpp")
-    if force or not os.path.exists(DIAGNOSE) or os.path.getmtime(src) > os.path.getmtime(DIAGNOSE) or os.path.getmtime(SO) > os.path.getmtime(DIAGNOSE):
-        os.makedirs(os.path.dirname(DIAGNOSE), exist_ok=True)
-        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        cmd = [cxx, "-O2", "-std=c++17", src, "-L" + LIBDIR, "-lxee_b200", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../lib", "-o", DIAGNOSE]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    return DIAGNOSE
+    return _build_host_program("xee_diagnose.cpp", DIAGNOSE, force)
+
+
+def build_old_diagnose(force: bool = False) -> str:
+    """C++ re-host of the reference's legacy driver (csrc/xee_old_diagnose.cpp: TENDENCY efficiency decomposition)."""
+    return _build_host_program("xee_old_diagnose.cpp", OLD_DIAGNOSE, force)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -163,6 +163,29 @@ void solve_elliptic_impl(int* max_iter, const int* check_step, const int* conver
   xee_judge_error(err);                                        // :254
 }
 
+// Legacy 12-argument solve_elliptic (src/old-diagnose/xtt-lib/elliptic_tools.f90:93-300) on top of the current solver:
+//   strategy 1 = r1 only, converge_time 1;   strategy 2 = r2 only, converge_time 10, lost_rate 5.
+template <class T>
+void solve_elliptic_old_impl(const int* max_iter, int* strategy, T* strategy_r, const T* alpha, T* dat, const T* coe,
+                             const T* f, T* workspace, const int* nx, const int* ny, int* err, const int* debug) {
+  *err = 0;
+  if (*strategy != 1 && *strategy != 2) { *err = 1 << 8; fprintf(stderr, "xee_b200: legacy strategy %d (max-abs residual) is not provided\n", *strategy); return; }
+  // the legacy loop tests cnt == max_iter only on check sweeps, so the effective bound is the last multiple of 100
+  const int eff_max = (*max_iter / 100) * 100;
+  if (eff_max <= 0) { memcpy(workspace, dat, sizeof(T) * (size_t)*nx * *ny); return; }
+  PlanBase* p = new_plan_or_die(dtype_of<T>(), *nx, *ny, 1, 1);
+  if (p->set_coe_aos(coe, true)) die("solve_elliptic(old)");
+  xee_solve_params prm{};
+  prm.max_iter = eff_max; prm.check_step = 100; prm.alpha = (double)*alpha; prm.sync_every = 2;
+  if (*strategy == 1) { prm.r1 = (double)*strategy_r; prm.r2 = 0.0; prm.converge_time = 1; prm.lost_rate = 5; if (!(prm.r1 > 0)) prm.r1 = 1e-300; }
+  else { prm.r1 = 0.0; prm.r2 = (double)*strategy_r; prm.converge_time = 10; prm.lost_rate = 5; if (!(prm.r2 > 0)) prm.r2 = 1e-300; }
+  int iters = 0, e = 0; double r1o = 0, r2o = 0;
+  if (p->solve(dat, f, &prm, &iters, &r1o, &r2o, &e, nullptr, true, workspace, *debug == 1 ? 2 : 0)) die("solve_elliptic(old)");
+  delete p;
+  *err = e; *strategy = iters; *strategy_r = (T)r1o;
+  xee_judge_error(err);
+}
+
 template <class T>
 struct PhysConst {  // constants.f90:4-5 evaluated in T
   T g0 = T(9.8), theta0 = T(298.0), Rd = T(287.0), Cv, Cp;
@@ -225,6 +248,12 @@ void xee_solve_elliptic_f32(int* max_iter, const int* check_step, const int* con
 }
 void xee_solve_elliptic_f64(int* max_iter, const int* check_step, const int* converge_time, const int* lost_rate, double* r1, double* r2, const double* alpha, double* dat, const double* coe, const double* f, double* workspace, const int* nx, const int* ny, int* err, const int* debug) {
   solve_elliptic_impl<double>(max_iter, check_step, converge_time, lost_rate, r1, r2, alpha, dat, coe, f, workspace, nx, ny, err, debug);
+}
+void xee_solve_elliptic_old_f32(const int* max_iter, int* strategy, float* strategy_r, const float* alpha, float* dat, const float* coe, const float* f, float* workspace, const int* nx, const int* ny, int* err, const int* debug) {
+  solve_elliptic_old_impl<float>(max_iter, strategy, strategy_r, alpha, dat, coe, f, workspace, nx, ny, err, debug);
+}
+void xee_solve_elliptic_old_f64(const int* max_iter, int* strategy, double* strategy_r, const double* alpha, double* dat, const double* coe, const double* f, double* workspace, const int* nx, const int* ny, int* err, const int* debug) {
+  solve_elliptic_old_impl<double>(max_iter, strategy, strategy_r, alpha, dat, coe, f, workspace, nx, ny, err, debug);
 }
 void xee_judge_error(const int* err) {   // elliptic_tools.f90:333-358
   const int e = *err;
