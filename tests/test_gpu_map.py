@@ -69,3 +69,46 @@ def test_map_device_resident_entry_equals_host_entry():
     td = torch.zeros((len(heat), 8), dtype=torch.float64, device="cuda")
     m.run_dev(torch.from_numpy(heat).cuda(), td, prm)
     assert np.array_equal(td.cpu().numpy(), t_host)
+
+
+def test_full_size_map_shard_properties():
+    """BASELINE config 4 at full size on one GPU (a 128-location shard on 512x256): size-independent properties.
+    (1) every solve converged; (2) independent residual through apply() (= do_elliptic) is below tolerance;
+    (3) linearity: doubling Q0 doubles psi and leaves the efficiency unchanged; (4) boundary rows stay 0;
+    (5) Jacobi (reference algorithm, STRICT) on a sub-sample converges to the same fields (1e-8 rel. L2)."""
+    import torch
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.efficiency_map import EfficiencyMap
+    nr, nz, nb = 512, 256, 128
+    Lr, Lz = (0.0, 1.0e6), (0.0, 1.5e4)
+    A, B, C = W.vortex_fields(nr, nz, Lr, Lz)
+    heat = W.heating_lattice(64, 64, Lr, Lz, 2 * Lr[1] / (nr - 1), 2 * Lz[1] / (nz - 1))[np.linspace(0, 4095, nb).astype(int)]
+    prm = X.SolveParams(max_iter=2000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=2, stall_checks=20)
+    m = EfficiencyMap(A, B, C, Lr, Lz, nb, "f64", arith="fast", method="chebyshev", r1_rel=1e-12)
+    tab = m.run(heat, prm)
+    assert np.all(tab[:, 2] == 0)
+    psi = m.field("psi"); f = m.field("f")
+    assert np.all(psi[:, 0, :] == 0) and np.all(psi[:, -1, :] == 0) and np.all(psi[:, :, 0] == 0) and np.all(psi[:, :, -1] == 0)
+    heat2 = heat.copy(); heat2[:, 4] *= 2.0
+    tab2 = m.run(heat2, prm)
+    psi2 = m.field("psi")
+    assert np.allclose(tab2[:, 5], tab[:, 5], rtol=1e-9)                  # efficiency is scale-free
+    assert rel_l2(psi2, 2.0 * psi) < 1e-9
+    # independent residual: L psi - f through the APPLY kernel of a separate plan built from a, b, c on the device
+    from oracle import oracle as O
+    d = O.Domain(Lr, Lz, nr, nz); g = O.geometry(d, np.float64)
+    a, b, c = O.build_abc(A.astype(np.float64), B.astype(np.float64), C.astype(np.float64), d)
+    plan = X.Plan(nr, nz, 8, "f64", shared_coe=True, arith="strict")
+    plan.set_abc(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda(), g["dr"], g["dz"])
+    idx = np.linspace(0, nb - 1, 8).astype(int)
+    Lp = plan.apply(torch.from_numpy(psi2[idx]).cuda()).cpu().numpy()
+    res = np.sqrt(((Lp - 2.0 * f[idx])[:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2)))
+    assert np.all(res <= 2e-12 * np.sqrt(((2.0 * f[idx])[:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2))))
+    # the reference's own iteration on two of the locations
+    mj = EfficiencyMap(A, B, C, Lr, Lz, 2, "f64", arith="strict", method="jacobi", r1_rel=1e-12)
+    tj = mj.run(heat[[3, 77]], X.SolveParams(max_iter=5000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=3))
+    pj = mj.field("psi")
+    assert np.all(tj[:, 2] == 0) and np.all(tj[:, 0] > 50 * tab[[3, 77], 0])
+    assert rel_l2(pj[0], psi[3]) < 1e-8 and rel_l2(pj[1], psi[77]) < 1e-8
+    assert np.allclose(tj[:, 5], tab[[3, 77], 5], rtol=1e-6)              # efficiency within 1e-6 relative
