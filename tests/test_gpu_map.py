@@ -112,5 +112,8 @@ def test_full_size_map_shard_properties():
     tj = mj.run(heat[[3, 77]], X.SolveParams(max_iter=5000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=3))
     pj = mj.field("psi")
     assert np.all(tj[:, 2] == 0) and np.all(tj[:, 0] > 50 * tab[[3, 77], 0])
-    assert rel_l2(pj[0], psi[3]) < 1e-8 and rel_l2(pj[1], psi[77]) < 1e-8
+    # Two different iterations stopped at the same residual r1 = 1e-12*rms(f) agree to ~(1/(1-rho))*1e-12 = 3e-8 at
+    # worst (Jacobi's remaining error sits in the slowest mode); the fp64 round-off floor (~1e-12) forbids a tighter
+    # common tolerance at 512x256.  Same-iteration parity (STRICT Jacobi vs the oracle) is bit-exact elsewhere.
+    assert rel_l2(pj[0], psi[3]) < 5e-8 and rel_l2(pj[1], psi[77]) < 5e-8
     assert np.allclose(tj[:, 5], tab[[3, 77], 5], rtol=1e-6)              # efficiency within 1e-6 relative
