@@ -408,3 +408,32 @@ def test_resident_solver_matches_direct_kernel_bitwise(name, shape, nb):
     plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=True, arith="strict", kernel=3); plan.set_coe_aos(coe)
     psi = torch.from_numpy(P).cuda(); plan.solve(psi, torch.from_numpy(F).cuda(), cases[0][2])
     assert np.array_equal(psi.cpu().numpy(), rb["dat"])
+
+
+@pytest.mark.parametrize("name", ["f32", "f64"])
+@pytest.mark.parametrize("shape,nb", [((140, 70), 7), ((512, 256), 3), ((260, 13), 9)])
+def test_tma_kernel_with_one_operator_per_solve(name, shape, nb):
+    """v2 with the operator planes travelling through the TMA stage (time-series shape) against v1: bit-identical."""
+    torch, X, O = _mods()
+    dt = DTS[name]; nx, ny = shape
+    coes, F, P = [], [], []
+    for k in range(nb):
+        a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=1000 + 13 * k + nx)
+        coes.append(O.cal_coe(a * dt(1 + 0.3 * k), b, c * dt(1 + 0.2 * k), 1.0, 0.5, nx, ny)[0]); F.append(f); P.append(x0)
+    coe = np.stack(coes); F = np.stack(F); P = np.stack(P)
+    for arith, method, prm in (("strict", "jacobi", X.SolveParams(max_iter=43, check_step=10, converge_time=10, r1=1e-30, r2=1.0, alpha=0.9)),
+                               ("fast", "chebyshev", X.SolveParams(max_iter=60, check_step=10, converge_time=10, r1=1e-30, r2=1.0, rho_jacobi=0.97))):
+        res = {}
+        for kern in (1, 2):
+            plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=False, arith=arith, method=method, kernel=kern)
+            plan.set_coe_aos(coe)
+            psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+            out = plan.solve(psi, ft, prm)
+            res[kern] = (psi.cpu().numpy(), out)
+            plan.close()
+        assert np.array_equal(res[1][0], res[2][0]), (arith, method)
+        assert np.allclose(res[1][1]["r1"], res[2][1]["r1"], rtol=1e-12 if name == "f64" else 1e-5)
+    rb = O.solve_batch(43, 10, 10, 5, 1e-30, 1.0, 0.9, P, coe, F, threads=4)
+    plan = X.Plan(nx, ny, nbatch=nb, dtype=name, shared_coe=False, arith="strict", kernel=2); plan.set_coe_aos(coe)
+    psi = torch.from_numpy(P).cuda(); plan.solve(psi, torch.from_numpy(F).cuda(), X.SolveParams(max_iter=43, check_step=10, converge_time=10, r1=1e-30, r2=1.0, alpha=0.9))
+    assert np.array_equal(psi.cpu().numpy(), rb["dat"])

@@ -138,7 +138,8 @@ struct Plan : PlanBase {
   // v2 (TMA) sweep kernel: launch geometry + tensor maps of the buffers of the current call
   bool use_tma = false;
   int tma_tiles_x = 0, tma_tiles_y = 0, tma_chunk = 1, tma_nchunks = 1, tma_grid = 1, tma_nstage = 6, num_sms = 148;
-  CUtensorMap map_halo[2]{}, map_plain[2]{}, map_f{};
+  CUtensorMap map_halo[2]{}, map_plain[2]{}, map_f{}, map_coe{};
+  bool map_coe_ready = false;
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
 
   int init() {
@@ -180,8 +181,8 @@ struct Plan : PlanBase {
     // Kernel variant: 1 = v1 direct, 2 = v2 TMA pipeline.  auto: TMA for shared-operator batches whose rows are
     // 16-byte multiples (TMA global-stride rule); everything else takes the direct kernel.
     int want = d.kernel > 0 ? d.kernel : env_int("XEE_KERNEL", 0);
-    const bool tma_ok = d.shared_coe && ((size_t)d.nx * sizeof(T)) % 16 == 0 && d.nx >= 8 && d.ny >= 4;
-    if (want == 2 && !tma_ok) return fail("xee: kernel=2 (TMA) needs a shared operator and nx*sizeof(real) % 16 == 0");
+    const bool tma_ok = ((size_t)d.nx * sizeof(T)) % 16 == 0 && d.nx >= 8 && d.ny >= 4;
+    if (want == 2 && !tma_ok) return fail("xee: kernel=2 (TMA) needs nx*sizeof(real) % 16 == 0");
     use_tma = (want == 2) || (want == 0 && tma_ok && (long long)d.nbatch * d.nx * d.ny >= (1 << 16));
     if (use_tma) {
       tma_tiles_x = (d.nx - 2 + tma::TW - 1) / tma::TW;
@@ -201,6 +202,7 @@ struct Plan : PlanBase {
       tma_nchunks = (d.nbatch + tma_chunk - 1) / tma_chunk;
       tma_grid = (int)std::min<long long>(grid_cap, (long long)nt * tma_nchunks);
       tma_nstage = std::max(2, std::min(env_int("XEE_TMA_STAGES", 6), tma::NSTAGE_MAX));
+      if (!d.shared_coe) tma_nstage = 2;   // the operator tiles travel with every stage: 2 x ~110 KB (fp64)
       if (nt > ntiles) return fail("xee: internal: partial buffer too small for the TMA tiling");
     }
     return 0;
@@ -240,6 +242,27 @@ struct Plan : PlanBase {
         encode_map(&map_f, f, d.nx, d.ny, nb, hw, tma::TH))
       return 1;
     map_ptrs[0] = x0; map_ptrs[1] = x1buf; map_ptrs[2] = f;
+    if (!d.shared_coe && !map_coe_ready) {
+      if (encode_map4(&map_coe, coe, d.nx, d.ny, kPlanes, nsets, hw, tma::TH, kPlanes)) return 1;
+      map_coe_ready = true;
+    }
+    return 0;
+  }
+  static int encode_map4(CUtensorMap* m, const void* base, int nx, int ny, int np, int ns, int box_w, int box_h, int box_p) {
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    XEE_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p) return fail("xee: cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)np, (cuuint64_t)ns};
+    const cuuint64_t strides[3] = {(cuuint64_t)nx * sizeof(T), (cuuint64_t)nx * ny * sizeof(T), (cuuint64_t)nx * ny * np * sizeof(T)};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = ((Fn)p)(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                               const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "xee: cuTensorMapEncodeTiled(4D) failed (%d)", (int)r); return fail(b); }
     return 0;
   }
   ~Plan() override {
@@ -321,21 +344,23 @@ struct Plan : PlanBase {
     if (check) sweep_direct_kernel<T, ARITH, MODE, true><<<g, blk, 0, s>>>(a);
     else sweep_direct_kernel<T, ARITH, MODE, false><<<g, blk, 0, s>>>(a);
   }
-  template <int ARITH, int MODE, bool CHECK>
+  template <int ARITH, int MODE, bool CHECK, bool PERSOLVE>
   int launch_tma_inst(const TmaSweepArgs<T>& P, const CUtensorMap& ms, const CUtensorMap& mp, cudaStream_t s) {
-    constexpr int stage = tma::Cfg<T>::PSI_BYTES + tma::Cfg<T>::FLD_BYTES + (MODE == MODE_CHEBYSHEV ? tma::Cfg<T>::FLD_BYTES : 0);
+    constexpr int coe_off = tma::Cfg<T>::PSI_BYTES + tma::Cfg<T>::FLD_BYTES + (MODE == MODE_CHEBYSHEV ? tma::Cfg<T>::FLD_BYTES : 0);
+    constexpr int stage = coe_off + (PERSOLVE ? (kPlanes * tma::Cfg<T>::FLD_RAW + 127) / 128 * 128 : 0);
     const size_t smem = (size_t)stage * P.nstage;
     static bool attr_done = false;
     if (!attr_done) {
-      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_done = true;
     }
-    sweep_tma_kernel<T, ARITH, MODE, CHECK><<<tma_grid, tma::NTHREADS, smem, s>>>(P, ms, mp, map_f);
+    sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE><<<tma_grid, tma::NTHREADS, smem, s>>>(P, ms, mp, map_f, map_coe);
     return 0;
   }
   template <int ARITH, int MODE>
   int launch_tma_mode(const TmaSweepArgs<T>& P, const CUtensorMap& ms, const CUtensorMap& mp, bool check, cudaStream_t s) {
-    return check ? launch_tma_inst<ARITH, MODE, true>(P, ms, mp, s) : launch_tma_inst<ARITH, MODE, false>(P, ms, mp, s);
+    if (d.shared_coe) return check ? launch_tma_inst<ARITH, MODE, true, false>(P, ms, mp, s) : launch_tma_inst<ARITH, MODE, false, false>(P, ms, mp, s);
+    return check ? launch_tma_inst<ARITH, MODE, true, true>(P, ms, mp, s) : launch_tma_inst<ARITH, MODE, false, true>(P, ms, mp, s);
   }
   int launch_sweep_tma(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
     TmaSweepArgs<T> P{};

@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 }  // namespace tma
 
@@ -76,15 +83,20 @@ struct TmaSweepArgs {
   int nstage;
 };
 
-template <class T, int ARITH, int MODE, bool CHECK>
+// PERSOLVE = one operator per solve (time series): the 10 operator planes of the tile arrive through the same TMA
+// stage as psi and f (one 4-D box [1][10][TH][HALO_W]) and are read from shared memory instead of registers.
+template <class T, int ARITH, int MODE, bool CHECK, bool PERSOLVE>
 __global__ void __launch_bounds__(tma::NTHREADS, 1)
     sweep_tma_kernel(const TmaSweepArgs<T> P, const __grid_constant__ CUtensorMap map_src,
-                     const __grid_constant__ CUtensorMap map_prev, const __grid_constant__ CUtensorMap map_f) {
+                     const __grid_constant__ CUtensorMap map_prev, const __grid_constant__ CUtensorMap map_f,
+                     const __grid_constant__ CUtensorMap map_coe) {
   using namespace tma;
   using R = Rn<T>;
   using C = Cfg<T>;
   constexpr bool CHEB = (MODE == MODE_CHEBYSHEV);
-  constexpr int STAGE_BYTES = C::PSI_BYTES + C::FLD_BYTES + (CHEB ? C::FLD_BYTES : 0);
+  constexpr int COE_OFF = C::PSI_BYTES + C::FLD_BYTES + (CHEB ? C::FLD_BYTES : 0);
+  constexpr int COE_RAW = kPlanes * C::FLD_RAW;
+  constexpr int STAGE_BYTES = COE_OFF + (PERSOLVE ? (COE_RAW + 127) / 128 * 128 : 0);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NSTAGE_MAX], empty_bar[NSTAGE_MAX];
   __shared__ double red[NCONS / 32];
@@ -116,7 +128,8 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
           const uint32_t ph = (it / nstage) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem_raw + (size_t)s * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], (uint32_t)((TH + 2) * C::HALO_W * sizeof(T) + C::FLD_RAW + (CHEB ? C::FLD_RAW : 0)));
+          mbar_expect_tx(&full_bar[s], (uint32_t)((TH + 2) * C::HALO_W * sizeof(T) + C::FLD_RAW + (CHEB ? C::FLD_RAW : 0) + (PERSOLVE ? COE_RAW : 0)));
+          if (PERSOLVE) tma_load_4d(st + COE_OFF, &map_coe, i0 - 1, j0, 0, n, &full_bar[s]);
           tma_load_3d(st, &map_src, i0 - 1, j0 - 1, n, &full_bar[s]);
           tma_load_3d(st + C::PSI_BYTES, &map_f, i0 - 1, j0, n, &full_bar[s]);
           if (CHEB) tma_load_3d(st + C::PSI_BYTES + C::FLD_BYTES, &map_prev, i0 - 1, j0, n, &full_bar[s]);
@@ -143,9 +156,11 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
       const int gj = j0 + rg * RPT + r;
       valid[r] = (gi < a.nx - 1) && (gj < a.ny - 1);
       off[r] = valid[r] ? (size_t)gj * a.nx + gi : (size_t)a.nx + 1;
+      if (!PERSOLVE) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) c[r][k] = __ldg(a.coe + k * nn + off[r]);
-      rcp[r] = __ldg(a.coe + 9 * nn + off[r]);
+        for (int k = 0; k < 9; ++k) c[r][k] = __ldg(a.coe + k * nn + off[r]);
+        rcp[r] = __ldg(a.coe + 9 * nn + off[r]);
+      }
     }
     for (int n = n0; n < n1; ++n) {
       if (a.done != nullptr && a.done[n]) continue;
@@ -168,6 +183,12 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
       for (int r = 0; r < RPT; ++r) {
         fv[r] = sf[(rg * RPT + r) * C::HALO_W + col + 1];
         xm[r] = CHEB ? sv[(rg * RPT + r) * C::HALO_W + col + 1] : T(0);
+        if (PERSOLVE) {
+          const T* sc = reinterpret_cast<const T*>(st + COE_OFF) + (rg * RPT + r) * C::HALO_W + col + 1;   // [10][TH][HALO_W]
+#pragma unroll
+          for (int k = 0; k < 9; ++k) c[r][k] = sc[k * TH * C::HALO_W];
+          rcp[r] = sc[9 * TH * C::HALO_W];
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);     // stage consumed: everything is in registers now
@@ -182,8 +203,9 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
         if (!CHEB) {
           out = jacobi_update<T, ARITH>(p[4], res, a.alpha, c[r][4], rcp[r]);
         } else {
+          const T om = (PERSOLVE && a.rho_ps) ? (T)cheb_omega(a.cheb_k, (double)a.rho_ps[n]) : a.omega;
           const T xj = jacobi_update<T, ARITH>(p[4], res, T(1), c[r][4], rcp[r]);
-          out = R::fma(a.omega, xj - xm[r], xm[r]);
+          out = R::fma(om, xj - xm[r], xm[r]);
         }
         if (valid[r]) {
           a.dst[(size_t)n * nn + off[r]] = out;
