@@ -212,7 +212,8 @@ def run_ours(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = P.launch_count()
-    sweep_ms, sweep_launches = m.sweep_kernel_stats()
+    sweep_ms, sweeps_done = m.sweep_kernel_stats()
+    variant, sweeps_per_pass, sweep_launches = m.kernel_info()
     tab = table_t.cpu().numpy()
     clocks = sampler.finish() if sampler else None
     ms_per_step = ms_total / args.steps
@@ -227,10 +228,15 @@ def run_ours(args):
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     k = workload_constants()
-    traffic = k.get("sweep_kernel_dram_bytes_per_launch")
+    # dram bytes of ONE launch of this variant from its ncu --set full capture (profiles/), None if not captured yet
+    traffic = k.get(f"sweep_kernel_dram_bytes_per_launch_v{variant}", k.get("sweep_kernel_dram_bytes_per_launch") if variant == 2 else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "sweep (K3/K4)",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": {1: "sweep_direct_kernel (v1)", 2: "sweep_tma_kernel (v2)", 3: "solve_resident_kernel (v3)",
+                           4: "sweep_tb_kernel (v4, temporal blocking)"}.get(variant, "sweep") + " (K3/K4)",
+                "sweeps_per_launch_T": sweeps_per_pass,
                 "avg_launch_us": sweep_ms / max(sweep_launches, 1) * 1e3, "launches": sweep_launches,
+                "avg_sweep_us": sweep_ms / max(sweeps_done, 1) * 1e3, "sweeps": sweeps_done,
                 "algorithmic_bytes_per_point_sweep": b_alg, "kernel_share_of_step": sweep_ms / ms_total,
                 "sweeps_per_solve": [float(tab[:, 0].min()), float(tab[:, 0].max())]}
     m.close(); del heat_t, table_t

@@ -165,8 +165,11 @@ int xee_plan_apply_dev(xee_plan* p, const void* psi_dev, void* out_dev, void* st
 void xee_release_cached_memory(void);
 /* Kernel-launch counter (bench.py's gpu_launches): launches issued by this library since reset. */
 long long xee_launch_count(int reset);
-/* Time (ms, CUDA events on the plan's stream) and launches of the dominant sweep kernel since reset. */
-int xee_sweep_kernel_stats(xee_plan* p, double* ms_total, long long* launches, int reset);
+/* Time (ms, CUDA events on the plan's stream) spent in the dominant sweep kernel and SWEEPS it performed since reset. */
+int xee_sweep_kernel_stats(xee_plan* p, double* ms_total, long long* sweeps, int reset);
+/* Sweep-kernel variant of the last solve (1 direct, 2 TMA pipeline, 3 resident, 4 temporal blocking), the sweeps one
+ * launch of it performs (>1 only for variant 4) and its launches since the last stats reset. */
+int xee_plan_kernel_info(xee_plan* p, int* variant, int* sweeps_per_pass, long long* kernel_launches);
 
 /* Post-processing on device fields (K5/K6), batch-wide.  geometry arrays are DEVICE pointers of the plan dtype. */
 int xee_eta_dev(int dtype, const void* rchi, void* eta, const void* ra, const void* rcuva, const void* rho,
@@ -204,7 +207,8 @@ int xee_map_run_host(xee_map* m, const double* heat_host, const xee_solve_params
 int xee_map_run_dev(xee_map* m, const double* heat_dev, const xee_solve_params* prm, double* table_dev, void* stream);
 /* which: 0 psi [nheat][nz][nr], 1 f, 2 theta_B [(nz-1)][(nr-1)], 3 eta [nz][nr-1], 4 chi.  Plan dtype, HOST out. */
 int xee_map_get_field(xee_map* m, int which, void* host_out);
-int xee_map_sweep_kernel_stats(xee_map* m, double* ms_total, long long* launches, int reset);
+int xee_map_sweep_kernel_stats(xee_map* m, double* ms_total, long long* sweeps, int reset);
+int xee_map_kernel_info(xee_map* m, int* variant, int* sweeps_per_pass, long long* kernel_launches);
 
 /* =====================================================================================
  * Part 4 - time-series diagnosis (BASELINE config 5): one vortex snapshot = one operator per
@@ -227,7 +231,8 @@ int xee_series_destroy(xee_series* s);
 int xee_series_run_host(xee_series* s, const double* params_host, const xee_solve_params* prm, double* table_host);
 /* which: 0 psi, 1 f, 2 theta_B, 3 u (C grid), 4 w (A grid), 5 A, 6 B, 7 C, 8 m2 (B grid); all [nsnap][...], plan dtype */
 int xee_series_get_field(xee_series* s, int which, void* host_out);
-int xee_series_sweep_kernel_stats(xee_series* s, double* ms_total, long long* launches, int reset);
+int xee_series_sweep_kernel_stats(xee_series* s, double* ms_total, long long* sweeps, int reset);
+int xee_series_kernel_info(xee_series* s, int* variant, int* sweeps_per_pass, long long* kernel_launches);
 
 #ifdef __cplusplus
 }

@@ -321,6 +321,30 @@ __global__ void select_result_kernel(T* __restrict__ x0, T* __restrict__ x1, con
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nn; q += (long long)gridDim.x * blockDim.x) a[q] = b[q];
 }
 
+// Final gather of the temporally blocked solver (v4).  Pass p reads the iterate pair p&1 and writes the other one
+// (pair 0 = (x0, x1), pair 1 = (x2, x3), each (latest, previous)); a solve that stopped after `iters` sweeps has been
+// through npass = (iters / check_step) * ceil(check_step / tb) + ceil((iters % check_step) / tb) passes.  Leaves the
+// result in x0 and in x1 what the reference leaves in `workspace` (elliptic_tools.f90:259-264: the penultimate iterate
+// when the sweep count is even, a copy of the result when it is odd).
+template <class T>
+__global__ void select_result_tb_kernel(T* __restrict__ x0, T* __restrict__ x1, const T* __restrict__ x2,
+                                        const T* __restrict__ x3, const int* __restrict__ iters, long long nn,
+                                        int check_step, int tb) {
+  const int n = blockIdx.y;
+  const int it = iters[n];
+  const int npass = (it / check_step) * ((check_step + tb - 1) / tb) + ((it % check_step) + tb - 1) / tb;
+  const bool pair1 = npass & 1, odd = it & 1;
+  if (!pair1 && !odd) return;
+  T* a = x0 + (size_t)n * nn; T* b = x1 + (size_t)n * nn;
+  const T* sn = pair1 ? x2 + (size_t)n * nn : a;
+  const T* sp = pair1 ? x3 + (size_t)n * nn : b;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nn; q += (long long)gridDim.x * blockDim.x) {
+    const T vn = sn[q], vp = sp[q];
+    a[q] = vn;
+    b[q] = odd ? vn : vp;
+  }
+}
+
 // ------------------------------------------------------------------------------------ K5
 // eta = d_rcuvdr_O2A(rchi) * g0 / (rho*Cp*exner*theta0)      quick-tools1.f90:1-13, quick-tools2.f90:59-85
 template <class T>

@@ -215,7 +215,14 @@ int xee_map_sweep_kernel_stats(xee_map* m, double* ms, long long* launches, int 
   PlanBase* p = m->impl->plan();
   if (ms) *ms = p->sweep_ms;
   if (launches) *launches = p->sweep_launches;
-  if (reset) { p->sweep_ms = 0; p->sweep_launches = 0; }
+  if (reset) { p->sweep_ms = 0; p->sweep_launches = 0; p->kernel_launches = 0; }
+  return 0;
+}
+int xee_map_kernel_info(xee_map* m, int* variant, int* sweeps_per_pass, long long* kernel_launches) {
+  PlanBase* p = m->impl->plan();
+  if (variant) *variant = p->variant_used;
+  if (sweeps_per_pass) *sweeps_per_pass = p->depth_used;
+  if (kernel_launches) *kernel_launches = p->kernel_launches;
   return 0;
 }
 }  // extern "C"

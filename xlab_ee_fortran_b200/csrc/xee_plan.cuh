@@ -14,6 +14,7 @@
 
 #include "xee_kernels.cuh"
 #include "xee_sweep_tma.cuh"
+#include "xee_sweep_tb.cuh"
 #include "xee_resident.cuh"
 
 namespace xee {
@@ -113,7 +114,9 @@ struct PlanBase {
   virtual int apply(const void* psi, void* out, cudaStream_t s) = 0;
   virtual int coe_to_aos_host(void* coe_host) = 0;
   double sweep_ms = 0.0;
-  long long sweep_launches = 0;
+  long long sweep_launches = 0;      // sweeps performed (v4 does up to tb_depth of them per kernel launch)
+  long long kernel_launches = 0;     // launches of the sweep kernel
+  int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..4) and its sweeps per pass
 };
 
 template <class T>
@@ -141,6 +144,12 @@ struct Plan : PlanBase {
   CUtensorMap map_halo[2]{}, map_plain[2]{}, map_f{}, map_coe{};
   bool map_coe_ready = false;
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
+  // v4 (temporal blocking) sweep kernel: two more iterate buffers (passes cannot update in place), tiling, maps
+  bool use_tb = false;
+  int tb_depth = 4, tb_tiles_x = 0, tb_tiles_y = 0, tb_chunk = 1, tb_nchunks = 1, tb_grid = 1;
+  T *x2 = nullptr, *x3 = nullptr;
+  CUtensorMap map_tb[4]{}, map_tb_f{};
+  const void* map_tb_ptrs[3] = {nullptr, nullptr, nullptr};
 
   int init() {
     TraceTimer tt("plan init");
@@ -205,9 +214,42 @@ struct Plan : PlanBase {
       if (!d.shared_coe) tma_nstage = 2;   // the operator tiles travel with every stage: 2 x ~110 KB (fp64)
       if (nt > ntiles) return fail("xee: internal: partial buffer too small for the TMA tiling");
     }
+    // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
+    // divisions, where the redundant halo work of overlapping tiles costs more than the saved traffic).
+    tb_depth = std::max(1, std::min(env_int("XEE_TB", 4), std::min(tb::TBMAX, tb::H / 2 - 1)));
+    if (sizeof(T) == 4 && (tb_depth & 1)) tb_depth += 1;    // tile origins must stay 16-byte aligned (4 floats)
+    const bool tb_ok = tma_ok && d.shared_coe;
+    if (want == 4 && !tb_ok) return fail("xee: kernel=4 (temporal blocking) needs a shared operator and nx*sizeof(real) % 16 == 0");
+    use_tb = (want == 4) || (want == 0 && tb_ok && d.arith == XEE_ARITH_FAST && d.nbatch >= 32 &&
+                             (long long)d.nbatch * d.nx * d.ny >= (1 << 22));
+    if (use_tb) {
+      const int sx = tb::W - 2 * tb_depth, sy = tb::H - 2 * tb_depth;
+      tb_tiles_x = d.nx <= tb::W ? 1 : (d.nx - tb::W + sx - 1) / sx + 1;
+      tb_tiles_y = d.ny <= tb::H ? 1 : (d.ny - tb::H + sy - 1) / sy + 1;
+      const int nt = tb_tiles_x * tb_tiles_y;
+      // chunk = solves per work unit: the operator registers are reloaded (from L2) once per unit, worth ~2 solves
+      long long best = -1; tb_chunk = 1;
+      const int chmax = std::min(env_int("XEE_TB_CHUNK", 64), d.nbatch), chmin = std::min(8, chmax);
+      for (int ch = chmax; ch >= chmin; --ch) {
+        const int nch = (d.nbatch + ch - 1) / ch;
+        const long long units = (long long)nt * nch;
+        const int g = (int)std::min<long long>(num_sms, units);
+        const long long makespan = ((units + g - 1) / g) * (ch + 2);
+        if (best < 0 || makespan < best) { best = makespan; tb_chunk = ch; }
+      }
+      tb_nchunks = (d.nbatch + tb_chunk - 1) / tb_chunk;
+      tb_grid = (int)std::min<long long>(num_sms, (long long)nt * tb_nchunks);
+      if (nt > ntiles) {   // the residual partials are per (solve, tile)
+        pool_free(partial); partial = nullptr;
+        XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
+      }
+      XEE_CHECK(pool_alloc(&x2, sizeof(T) * nn * d.nbatch));
+      XEE_CHECK(pool_alloc(&x3, sizeof(T) * nn * d.nbatch));
+    }
     return 0;
   }
   int sweep_ntiles() const { return use_tma ? tma_tiles_x * tma_tiles_y : ntiles; }
+  int tb_ntiles() const { return tb_tiles_x * tb_tiles_y; }
 
   // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).
   static int encode_map(CUtensorMap* m, const void* base, int nx, int ny, int nb, int box_w, int box_h) {
@@ -266,7 +308,7 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -387,6 +429,63 @@ struct Plan : PlanBase {
     return 0;
   }
 
+  // ---- v4: temporal blocking.  Iterates live in two buffer pairs (new, prev): pair 0 = (x0, x1), pair 1 = (x2, x3);
+  // pass p reads pair p&1 and writes the other one.
+  int prepare_tb_maps(const T* x0, const T* f, int nb) {
+    if (map_tb_ptrs[0] == x0 && map_tb_ptrs[1] == f && map_tb_ptrs[2] == x1) return 0;
+    if (((uintptr_t)x0 | (uintptr_t)f | (uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3) & 15) return fail("xee: TMA path needs 16-byte aligned field buffers");
+    const T* bufs[4] = {x0, x1, x2, x3};
+    for (int q = 0; q < 4; ++q)
+      if (encode_map(&map_tb[q], bufs[q], d.nx, d.ny, nb, tb::W, tb::H)) return 1;
+    if (encode_map(&map_tb_f, f, d.nx, d.ny, nb, tb::W, tb::H)) return 1;
+    map_tb_ptrs[0] = x0; map_tb_ptrs[1] = f; map_tb_ptrs[2] = x1;
+    return 0;
+  }
+  template <int ARITH, int MODE, bool CHECK>
+  int launch_tb_inst(const TbArgs<T>& A, const CUtensorMap& mx, const CUtensorMap& mxm, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      XEE_CHECK(cudaFuncSetAttribute(sweep_tb_kernel<T, ARITH, MODE, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb::Cfg<T>::SMEM_BYTES));
+      attr_done = true;
+    }
+    sweep_tb_kernel<T, ARITH, MODE, CHECK><<<tb_grid, tb::NT, tb::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, map_tb_f);
+    return 0;
+  }
+  template <int ARITH, int MODE>
+  int launch_tb_mode(const TbArgs<T>& A, const CUtensorMap& mx, const CUtensorMap& mxm, bool check, cudaStream_t s) {
+    return check ? launch_tb_inst<ARITH, MODE, true>(A, mx, mxm, s) : launch_tb_inst<ARITH, MODE, false>(A, mx, mxm, s);
+  }
+  // One pass: sweeps first_cnt .. first_cnt+t-1 (1-based sweep numbers) of every solve that is not done.
+  int launch_tb_pass(T* x0, int pass_idx, int first_cnt, int t, bool check, T alpha, int mode, const int* done, cudaStream_t s) {
+    T* bufs[4] = {x0, x1, x2, x3};
+    const int pin = pass_idx & 1, pout = pin ^ 1;
+    TbArgs<T> A{};
+    A.coe = coe; A.out_new = bufs[2 * pout]; A.out_prev = bufs[2 * pout + 1];
+    A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = d.nbatch;
+    A.nsweeps = t; A.tbh = tb_depth; A.alpha = alpha;
+    for (int q = 0; q < t; ++q) A.omega[q] = mode == MODE_CHEBYSHEV ? (T)cheb_omega_host(first_cnt + q, cheb_rho) : T(1);
+    A.done = done; A.partial = partial;
+    A.tiles_x = tb_tiles_x; A.tiles_y = tb_tiles_y; A.nchunks = tb_nchunks; A.chunk = tb_chunk;
+    const CUtensorMap& mx = map_tb[2 * pin];
+    const CUtensorMap& mxm = map_tb[2 * pin + 1];
+    const bool strict = d.arith == XEE_ARITH_STRICT;
+    int rc;
+    if (mode == MODE_JACOBI) rc = strict ? launch_tb_mode<XEE_ARITH_STRICT, MODE_JACOBI>(A, mx, mxm, check, s) : launch_tb_mode<XEE_ARITH_FAST, MODE_JACOBI>(A, mx, mxm, check, s);
+    else rc = strict ? launch_tb_mode<XEE_ARITH_STRICT, MODE_CHEBYSHEV>(A, mx, mxm, check, s) : launch_tb_mode<XEE_ARITH_FAST, MODE_CHEBYSHEV>(A, mx, mxm, check, s);
+    if (rc) return rc;
+    XEE_LAUNCH_OK();
+    ++kernel_launches;
+    return 0;
+  }
+  // Boundary values and the first guess in every buffer (elliptic_tools.f90:166-171: workspace = dat).
+  int tb_seed_buffers(const T* x0, cudaStream_t s) {
+    const size_t fbytes = sizeof(T) * nn * d.nbatch;
+    XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(x2, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(x3, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+
   cudaEvent_t next_event() {
     if (ev_used == ev_pool.size()) {
       cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e);
@@ -464,11 +563,40 @@ struct Plan : PlanBase {
 
   int sweeps(void* psi, const void* f, double alpha, int nsw, double* rms, cudaStream_t s) override {
     T* x0 = (T*)psi;
+    const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
+    if (use_tb) {
+      if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;
+      if (tb_seed_buffers(x0, s) || prepare_tb_maps(x0, (const T*)f, d.nbatch)) return 1;
+      cudaEvent_t e0 = next_event(), e1 = next_event();
+      XEE_CHECK(cudaEventRecord(e0, s));
+      int cnt = 0, pass = 0;
+      while (cnt < nsw) {
+        const int t = std::min(tb_depth, nsw - cnt);
+        if (launch_tb_pass(x0, pass, cnt + 1, t, rms && cnt + t == nsw, (T)alpha, mode, nullptr, s)) return 1;
+        cnt += t; ++pass;
+      }
+      sweep_launches += nsw; variant_used = 4; depth_used = tb_depth;
+      XEE_CHECK(cudaEventRecord(e1, s));
+      if (pass & 1) XEE_CHECK(cudaMemcpyAsync(x0, x2, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
+      XEE_CHECK(cudaStreamSynchronize(s));
+      harvest_events();
+      if (rms && nsw > 0) {
+        const int nt = tb_ntiles();
+        std::vector<double> h((size_t)nt * d.nbatch);
+        XEE_CHECK(cudaMemcpy(h.data(), partial, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        const double N = (double)(d.nx - 2) * (d.ny - 2);
+        for (int n = 0; n < d.nbatch; ++n) {
+          double t = 0;
+          for (int q = 0; q < nt; ++q) t += h[(size_t)n * nt + q];
+          rms[n] = std::sqrt(t / N);
+        }
+      }
+      return 0;
+    }
     XEE_CHECK(cudaMemcpyAsync(x1, x0, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     if (prepare_maps(x0, x1, (const T*)f, d.nbatch)) return 1;
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
-    const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
     if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;
     for (int cnt = 1; cnt <= nsw; ++cnt) {
       const T* src = (cnt & 1) ? x0 : x1;
@@ -478,7 +606,7 @@ struct Plan : PlanBase {
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, rms && cnt == nsw, s)) return 1;
     }
-    sweep_launches += nsw;
+    sweep_launches += nsw; kernel_launches += nsw; variant_used = use_tma ? 2 : 1; depth_used = 1;
     XEE_CHECK(cudaEventRecord(e1, s));
     if (nsw & 1) XEE_CHECK(cudaMemcpyAsync(x0, x1, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     XEE_CHECK(cudaStreamSynchronize(s));
@@ -685,6 +813,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
     if (solve_resident(x0, fd, prm, check_step, converge_time, lost_rate, mode, s)) return 1;
+    ++kernel_launches; variant_used = 3; depth_used = 1;
     XEE_CHECK(cudaEventRecord(e1, s));
     std::vector<int> hi(nb), he(nb);
     std::vector<T> h1(nb), h2(nb);
@@ -718,8 +847,13 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     return 0;
   }
   // workspace = dat: both ping-pong buffers start as boundary + first guess (:166-171)
-  XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
-  if (prepare_maps(x0, x1, fd, nb)) return 1;
+  if (use_tb) { if (tb_seed_buffers(x0, s) || prepare_tb_maps(x0, fd, nb)) return 1; }
+  else {
+    XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
+    if (prepare_maps(x0, x1, fd, nb)) return 1;
+  }
+  int tb_pass = 0;
+  variant_used = use_tb ? 4 : use_tma ? 2 : 1; depth_used = use_tb ? tb_depth : 1;
   const int ninterior = (d.nx - 2) * (d.ny - 2);
   const int lookahead = prm->sync_every > 0 ? prm->sync_every : 1;
   int cnt = 0, check_idx = 0, printed = 0;
@@ -731,7 +865,13 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     const int chunk = std::min(to_check, max_iter - cnt);
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
-    for (int k = 0; k < chunk; ++k) {
+    for (int rem = use_tb ? chunk : 0; rem > 0;) {   // v4: passes of up to tb_depth sweeps, a check closes a pass
+      const int t = std::min(tb_depth, rem);
+      const bool check = ((cnt + t) % check_step) == 0;
+      if (launch_tb_pass(x0, tb_pass, cnt + 1, t, check, (T)prm->alpha, mode, st.done, s)) return 1;
+      cnt += t; rem -= t; ++tb_pass;
+    }
+    for (int k = 0; k < chunk && !use_tb; ++k) {
       ++cnt;
       const T* src = (cnt & 1) ? x0 : x1;   // sweep cnt reads the buffer written by sweep cnt-1
       T* dst = (cnt & 1) ? x1 : x0;
@@ -742,9 +882,10 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
       if (launch_sweep(a, mode, check, s)) return 1;
     }
     sweep_launches += chunk;
+    if (!use_tb) kernel_launches += chunk;
     XEE_CHECK(cudaEventRecord(e1, s));
     if ((cnt % check_step) == 0) {
-      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
+      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, use_tb ? tb_ntiles() : sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
                                                   lost_rate, max_iter, prm->detect_explode, prm->stall_checks);
       XEE_LAUNCH_OK();
       const int slot = check_idx & 3;
@@ -776,7 +917,8 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     XEE_LAUNCH_OK();
   }
   dim3 g((unsigned)std::min<size_t>((nn + 255) / 256, 64), nb);
-  select_result_kernel<T><<<g, 256, 0, s>>>(x0, x1, st.iters, (long long)nn, 1);
+  if (use_tb) select_result_tb_kernel<T><<<g, 256, 0, s>>>(x0, x1, x2, x3, st.iters, (long long)nn, check_step, tb_depth);
+  else select_result_kernel<T><<<g, 256, 0, s>>>(x0, x1, st.iters, (long long)nn, 1);
   XEE_LAUNCH_OK();
   if (host_io) {
     XEE_CHECK(cudaMemcpyAsync(psi, x0, fbytes, cudaMemcpyDeviceToHost, s));

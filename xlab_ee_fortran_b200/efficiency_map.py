@@ -87,6 +87,12 @@ class EfficiencyMap:
         _lib.lib().xee_map_sweep_kernel_stats(self._h, C.byref(ms), C.byref(n), C.c_int(int(reset)))
         return ms.value, n.value
 
+    def kernel_info(self):
+        """(variant 1..4, sweeps per kernel launch, kernel launches since the last stats reset) of the sweep kernel."""
+        v = C.c_int(0); d = C.c_int(0); n = C.c_longlong(0)
+        _lib.lib().xee_map_kernel_info(self._h, C.byref(v), C.byref(d), C.byref(n))
+        return v.value, d.value, n.value
+
 
 # ---------------------------------------------------------------------------------- sharding (SURVEY 8e)
 def partition(n_items: int, world: int, rank: int):
