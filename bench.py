@@ -222,7 +222,7 @@ def run_ours(args):
     n_floor = int((tab[:, 2] == 4).sum())
     # roofline of the dominant kernel: useful point-sweeps actually performed (per-solve sweep counts) x bytes
     interior = (NR - 2) * (NZ - 2)
-    fields = 4 if args.method == "chebyshev" else 3           # psi read, psi write, f read (+ psi_{k-1} for Chebyshev)
+    fields = 4 if args.method.endswith("chebyshev") else 3           # psi read, psi write, f read (+ psi_{k-1} for Chebyshev)
     b_alg = 8.0 * (fields + 9.0 / nloc)
     alg_bytes = float(tab[:, 0].sum()) * interior * b_alg * args.steps
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
@@ -233,7 +233,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "kernel": {1: "sweep_direct_kernel (v1)", 2: "sweep_tma_kernel (v2)", 3: "solve_resident_kernel (v3)",
-                           4: "sweep_tb_kernel (v4, temporal blocking)"}.get(variant, "sweep") + " (K3/K4)",
+                           4: "sweep_tb_kernel (v4, temporal blocking)", 5: "sweep_line_kernel (v5, segment-line relaxation)"}.get(variant, "sweep") + " (K3/K4)",
                 "sweeps_per_launch_T": sweeps_per_pass,
                 "avg_launch_us": sweep_ms / max(sweep_launches, 1) * 1e3, "launches": sweep_launches,
                 "avg_sweep_us": sweep_ms / max(sweeps_done, 1) * 1e3, "sweeps": sweeps_done,
@@ -303,7 +303,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nheat", type=int, default=512, help="heating locations (independent solves) per GPU")
-    ap.add_argument("--method", default="chebyshev", choices=["chebyshev", "jacobi"])
+    ap.add_argument("--method", default="chebyshev", choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi"])
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--max-iter", type=int, default=2000000)
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -112,6 +112,11 @@ void xee_cal_uw_f64(const double* rpsi, double* u, double* w, const double* ra, 
 #define XEE_ARITH_FAST 1   /* FMA + precomputed reciprocal (same fixed point, 1e-13 rel) */
 #define XEE_METHOD_JACOBI 0    /* the reference's weighted Jacobi                        */
 #define XEE_METHOD_CHEBYSHEV 1 /* Chebyshev-accelerated Jacobi (same residual definition)*/
+/* Segment-line relaxation along the radius (not in the reference): same discrete problem, residual and stop rule, but
+ * the correction solves coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i) exactly on segments of 8 radial points instead
+ * of dividing r by coe5.  Shared operator, FAST arithmetic only. */
+#define XEE_METHOD_LINE_JACOBI 2
+#define XEE_METHOD_LINE_CHEBYSHEV 3
 
 typedef struct xee_plan xee_plan;
 

@@ -15,6 +15,7 @@
 #include "xee_kernels.cuh"
 #include "xee_sweep_tma.cuh"
 #include "xee_sweep_tb.cuh"
+#include "xee_sweep_line.cuh"
 #include "xee_resident.cuh"
 
 namespace xee {
@@ -144,6 +145,14 @@ struct Plan : PlanBase {
   CUtensorMap map_halo[2]{}, map_plain[2]{}, map_f{}, map_coe{};
   bool map_coe_ready = false;
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
+  // v5 (segment-line relaxation, XEE_METHOD_LINE_*): Thomas factors, tiling, tensor-map cache
+  bool use_line = false;
+  T* linefac = nullptr;              // [2][ny][nx]
+  bool linefac_ready = false;
+  int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
+  struct LineMap { const void* ptr; int nb; int kind; CUtensorMap map; };
+  std::vector<LineMap> line_maps;    // kind 0: psi box (with halo), 1: f / psi_{k-1} box
+  bool method_is_cheb() const { return d.method == XEE_METHOD_CHEBYSHEV || d.method == XEE_METHOD_LINE_CHEBYSHEV; }
   // v4 (temporal blocking) sweep kernel: two more iterate buffers (passes cannot update in place), tiling, maps
   bool use_tb = false;
   int tb_depth = 4, tb_tiles_x = 0, tb_tiles_y = 0, tb_chunk = 1, tb_nchunks = 1, tb_grid = 1;
@@ -214,11 +223,38 @@ struct Plan : PlanBase {
       if (!d.shared_coe) tma_nstage = 2;   // the operator tiles travel with every stage: 2 x ~110 KB (fp64)
       if (nt > ntiles) return fail("xee: internal: partial buffer too small for the TMA tiling");
     }
+    // v5: segment-line relaxation is a METHOD, not a variant of the reference iteration: explicit request only.
+    use_line = d.method == XEE_METHOD_LINE_JACOBI || d.method == XEE_METHOD_LINE_CHEBYSHEV;
+    if (d.method < 0 || d.method > XEE_METHOD_LINE_CHEBYSHEV) return fail("xee: unknown method");
+    if (use_line) {
+      if (!d.shared_coe || d.arith != XEE_ARITH_FAST || !tma_ok)
+        return fail("xee: the line-relaxation methods need a shared operator, FAST arithmetic and nx*sizeof(real) % 16 == 0");
+      if (want != 0 && want != 5) return fail("xee: the line-relaxation methods run on sweep kernel 5 only");
+      use_tma = false;
+      ln_tiles_x = (d.nx + ln::TW - 1) / ln::TW; ln_tiles_y = (d.ny + ln::TH - 1) / ln::TH;
+      const int nt = ln_tiles_x * ln_tiles_y;
+      long long best = -1; ln_chunk = 1;
+      const int chmax = std::min(env_int("XEE_LINE_CHUNK", 32), d.nbatch), chmin = std::min(4, chmax);
+      for (int ch = chmax; ch >= chmin; --ch) {
+        const int nch = (d.nbatch + ch - 1) / ch;
+        const long long units = (long long)nt * nch;
+        const int g = (int)std::min<long long>(num_sms, units);
+        const long long makespan = ((units + g - 1) / g) * (ch + 1);
+        if (best < 0 || makespan < best) { best = makespan; ln_chunk = ch; }
+      }
+      ln_nchunks = (d.nbatch + ln_chunk - 1) / ln_chunk;
+      if (nt > ntiles) {
+        pool_free(partial); partial = nullptr;
+        XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
+      }
+      XEE_CHECK(pool_alloc(&linefac, sizeof(T) * 2 * nn));
+      want = 5;
+    } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
     // divisions, where the redundant halo work of overlapping tiles costs more than the saved traffic).
     tb_depth = std::max(1, std::min(env_int("XEE_TB", 4), std::min(tb::TBMAX, tb::H / 2 - 1)));
     if (sizeof(T) == 4 && (tb_depth & 1)) tb_depth += 1;    // tile origins must stay 16-byte aligned (4 floats)
-    const bool tb_ok = tma_ok && d.shared_coe;
+    const bool tb_ok = tma_ok && d.shared_coe && !use_line;
     if (want == 4 && !tb_ok) return fail("xee: kernel=4 (temporal blocking) needs a shared operator and nx*sizeof(real) % 16 == 0");
     use_tb = (want == 4) || (want == 0 && tb_ok && d.arith == XEE_ARITH_FAST && d.nbatch >= 32 &&
                              (long long)d.nbatch * d.nx * d.ny >= (1 << 22));
@@ -248,7 +284,7 @@ struct Plan : PlanBase {
     }
     return 0;
   }
-  int sweep_ntiles() const { return use_tma ? tma_tiles_x * tma_tiles_y : ntiles; }
+  int sweep_ntiles() const { return use_line ? ln_tiles_x * ln_tiles_y : use_tma ? tma_tiles_x * tma_tiles_y : ntiles; }
   int tb_ntiles() const { return tb_tiles_x * tb_tiles_y; }
 
   // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).
@@ -308,7 +344,7 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -337,7 +373,7 @@ struct Plan : PlanBase {
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     if (tmp) pool_free(tmp);
     cheb_rho = 0.0; rho_ps.clear();
-    return 0;
+    return line_factors();
   }
   int set_abc(const void* a, const void* b, const void* c, double dx, double dy) override {
     dim3 blk(64, 4), g((d.nx - 2 + 63) / 64, (d.ny - 2 + 3) / 4, nsets);
@@ -349,6 +385,15 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     cheb_rho = 0.0; rho_ps.clear();
+    return line_factors();
+  }
+  int line_factors() {   // Thomas factors of the radial segments (v5), once per operator
+    if (!use_line) return 0;
+    dim3 g(((d.nx + ln::SEG - 1) / ln::SEG + 63) / 64, d.ny);
+    line_factor_kernel<T><<<g, 64, 0, own_stream>>>(coe, linefac, d.nx, d.ny);
+    XEE_LAUNCH_OK();
+    XEE_CHECK(cudaStreamSynchronize(own_stream));
+    linefac_ready = true;
     return 0;
   }
   int coe_to_aos_host(void* coe_host) override {  // set 0 only (Fortran-facing cal_coe)
@@ -418,7 +463,46 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     return 0;
   }
+  // ---- v5: segment-line relaxation
+  int line_map(const void* ptr, int nb, int kind, CUtensorMap* out) {
+    for (auto& m : line_maps) if (m.ptr == ptr && m.nb == nb && m.kind == kind) { *out = m.map; return 0; }
+    if ((uintptr_t)ptr & 15) return fail("xee: TMA path needs 16-byte aligned field buffers");
+    if (line_maps.size() >= 16) line_maps.erase(line_maps.begin());
+    LineMap lm{ptr, nb, kind, {}};
+    if (kind == 0 ? encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::XW, ln::TH + 2) : encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::FW, ln::TH)) return 1;
+    line_maps.push_back(lm);
+    *out = lm.map;
+    return 0;
+  }
+  template <bool CHEB, bool CHECK>
+  int launch_line_inst(const LineArgs<T>& A, int grid, const CUtensorMap& mx, const CUtensorMap& mxm, const CUtensorMap& mf, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      XEE_CHECK(cudaFuncSetAttribute(sweep_line_kernel<T, CHEB, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln::Cfg<T>::SMEM_BYTES));
+      attr_done = true;
+    }
+    sweep_line_kernel<T, CHEB, CHECK><<<grid, ln::NT, ln::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, mf);
+    return 0;
+  }
+  int launch_sweep_line(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
+    if (!linefac_ready) return fail("xee: line relaxation: the operator has not been set");
+    CUtensorMap cx, cxm, cf;
+    if (line_map(a.src, a.nbatch, 0, &cx) || line_map(a.f, a.nbatch, 1, &cf) || line_map(a.dst, a.nbatch, 1, &cxm)) return 1;
+    LineArgs<T> A{};
+    A.coe = coe; A.fac = linefac; A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
+    A.alpha = a.alpha; A.omega = a.omega; A.rho_ps = a.rho_ps; A.cheb_k = a.cheb_k; A.done = a.done; A.partial = partial;
+    A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
+    A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
+    const int grid = (int)std::min<long long>(num_sms, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
+    int rc;
+    if (mode == MODE_CHEBYSHEV) rc = check ? launch_line_inst<true, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<true, false>(A, grid, cx, cxm, cf, s);
+    else rc = check ? launch_line_inst<false, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<false, false>(A, grid, cx, cxm, cf, s);
+    if (rc) return rc;
+    XEE_LAUNCH_OK();
+    return 0;
+  }
   int launch_sweep(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
+    if (use_line && mode != MODE_APPLY) return launch_sweep_line(a, mode, check, s);
     if (use_tma && mode != MODE_APPLY && a.nbatch == d.nbatch && (a.src == map_ptrs[0] || a.src == map_ptrs[1]))
       return launch_sweep_tma(a, mode, check, s);
     const bool strict = d.arith == XEE_ARITH_STRICT;
@@ -563,7 +647,7 @@ struct Plan : PlanBase {
 
   int sweeps(void* psi, const void* f, double alpha, int nsw, double* rms, cudaStream_t s) override {
     T* x0 = (T*)psi;
-    const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
+    const int mode = method_is_cheb() ? MODE_CHEBYSHEV : MODE_JACOBI;
     if (use_tb) {
       if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;
       if (tb_seed_buffers(x0, s) || prepare_tb_maps(x0, (const T*)f, d.nbatch)) return 1;
@@ -606,7 +690,7 @@ struct Plan : PlanBase {
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, rms && cnt == nsw, s)) return 1;
     }
-    sweep_launches += nsw; kernel_launches += nsw; variant_used = use_tma ? 2 : 1; depth_used = 1;
+    sweep_launches += nsw; kernel_launches += nsw; variant_used = use_line ? 5 : use_tma ? 2 : 1; depth_used = 1;
     XEE_CHECK(cudaEventRecord(e1, s));
     if (nsw & 1) XEE_CHECK(cudaMemcpyAsync(x0, x1, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     XEE_CHECK(cudaStreamSynchronize(s));
@@ -799,7 +883,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   const int converge_time = prm->converge_time > 0 ? prm->converge_time : 10;  // :136-139
   const int lost_rate = prm->lost_rate > 0 ? prm->lost_rate : 5;               // :141-144
   const int max_iter = prm->max_iter;
-  const int mode = d.method == XEE_METHOD_CHEBYSHEV ? MODE_CHEBYSHEV : MODE_JACOBI;
+  const int mode = method_is_cheb() ? MODE_CHEBYSHEV : MODE_JACOBI;
   if (mode == MODE_CHEBYSHEV) {
     if (prepare_cheb(prm->rho_jacobi, s)) return 1;
   }
@@ -807,7 +891,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   XEE_LAUNCH_OK();
   // v3: the whole loop in one cooperative launch (single / few solves that fit on the chip)
   int want_kernel = d.kernel > 0 ? d.kernel : env_int("XEE_KERNEL", 0);
-  const bool resident_ok = (d.shared_coe || nb == 1) && max_iter >= 1 && resident_fits();
+  const bool resident_ok = !use_line && (d.shared_coe || nb == 1) && max_iter >= 1 && resident_fits();
   if (want_kernel == 3 && !resident_ok) return fail("xee: kernel=3 (resident) needs a problem that fits: nbatch*strips <= SMs, <= 1536 points per strip");
   if (want_kernel == 3 || (want_kernel == 0 && resident_ok && nb <= 2)) {
     cudaEvent_t e0 = next_event(), e1 = next_event();
@@ -853,7 +937,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     if (prepare_maps(x0, x1, fd, nb)) return 1;
   }
   int tb_pass = 0;
-  variant_used = use_tb ? 4 : use_tma ? 2 : 1; depth_used = use_tb ? tb_depth : 1;
+  variant_used = use_line ? 5 : use_tb ? 4 : use_tma ? 2 : 1; depth_used = use_tb ? tb_depth : 1;
   const int ninterior = (d.nx - 2) * (d.ny - 2);
   const int lookahead = prm->sync_every > 0 ? prm->sync_every : 1;
   int cnt = 0, check_idx = 0, printed = 0;

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .plan import ARITH_FAST, ARITH_STRICT, CHEBYSHEV, F32, F64, JACOBI, SolveParams, _SolveParams
+from .plan import ARITH_FAST, ARITH_STRICT, CHEBYSHEV, F32, F64, JACOBI, METHODS, SolveParams, _SolveParams
 
 COLS = ("iters", "r1", "err", "sum_Q", "ke_gen", "efficiency", "sum_Qeta", "efficiency_eta")
 
@@ -40,7 +40,7 @@ class EfficiencyMap:
         self.nr, self.nz, self.nheat = nr, nz, int(nheat)
         self.np_dtype = np.float64 if dtype == "f64" else np.float32
         d = _MapDesc(F64 if dtype == "f64" else F32, nr, nz, self.nheat, density_mode,
-                     ARITH_STRICT if arith == "strict" else ARITH_FAST, CHEBYSHEV if method == "chebyshev" else JACOBI,
+                     ARITH_STRICT if arith == "strict" else ARITH_FAST, METHODS[method],
                      device, int(adjoint_check), (C.c_double * 2)(*Lr), (C.c_double * 2)(*Lz), float(r1_rel))
         self._h = C.c_void_p()
         p = lambda a: a.ctypes.data_as(C.c_void_p)

@@ -14,7 +14,8 @@ from . import _lib
 
 F32, F64 = 0, 1
 ARITH_STRICT, ARITH_FAST = 0, 1
-JACOBI, CHEBYSHEV = 0, 1
+JACOBI, CHEBYSHEV, LINE_JACOBI, LINE_CHEBYSHEV = 0, 1, 2, 3
+METHODS = {"jacobi": JACOBI, "chebyshev": CHEBYSHEV, "line_jacobi": LINE_JACOBI, "line_chebyshev": LINE_CHEBYSHEV}
 
 
 class _PlanDesc(C.Structure):
@@ -63,7 +64,7 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         d = _PlanDesc(self.dtype, self.nx, self.ny, self.nbatch, int(self.shared_coe),
                       ARITH_STRICT if arith == "strict" else ARITH_FAST,
-                      CHEBYSHEV if method == "chebyshev" else JACOBI, self.device.index, int(kernel))
+                      METHODS[method], self.device.index, int(kernel))
         self._h = C.c_void_p()
         L = _lib.lib()
         with torch.cuda.device(self.device):
