@@ -148,6 +148,7 @@ struct Plan : PlanBase {
   // v5 (segment-line relaxation, XEE_METHOD_LINE_*): Thomas factors, tiling, tensor-map cache
   bool use_line = false;
   T* linefac = nullptr;              // [2][ny][nx]
+  T* linepack = nullptr;             // operator + factors in tile/thread order
   bool linefac_ready = false;
   int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
   struct LineMap { const void* ptr; int nb; int kind; CUtensorMap map; };
@@ -248,6 +249,7 @@ struct Plan : PlanBase {
         XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
       }
       XEE_CHECK(pool_alloc(&linefac, sizeof(T) * 2 * nn));
+      XEE_CHECK(pool_alloc(&linepack, sizeof(T) * (size_t)nt * kLinePlanes * ln::SEG * ln::NT));
       want = 5;
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
@@ -344,7 +346,7 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -391,6 +393,8 @@ struct Plan : PlanBase {
     if (!use_line) return 0;
     dim3 g(((d.nx + ln::SEG - 1) / ln::SEG + 63) / 64, d.ny);
     line_factor_kernel<T><<<g, 64, 0, own_stream>>>(coe, linefac, d.nx, d.ny);
+    XEE_LAUNCH_OK();
+    line_pack_kernel<T><<<ln_tiles_x * ln_tiles_y, ln::NT, 0, own_stream>>>(coe, linefac, linepack, d.nx, d.ny, ln_tiles_x);
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     linefac_ready = true;
@@ -489,7 +493,7 @@ struct Plan : PlanBase {
     CUtensorMap cx, cxm, cf;
     if (line_map(a.src, a.nbatch, 0, &cx) || line_map(a.f, a.nbatch, 1, &cf) || line_map(a.dst, a.nbatch, 1, &cxm)) return 1;
     LineArgs<T> A{};
-    A.coe = coe; A.fac = linefac; A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
+    A.pack = linepack; A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
     A.alpha = a.alpha; A.omega = a.omega; A.rho_ps = a.rho_ps; A.cheb_k = a.cheb_k; A.done = a.done; A.partial = partial;
     A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
