@@ -30,8 +30,8 @@ int main(int argc, char** argv) {
   for (auto& p : x) { CK(cudaMalloc(&p, tot * 8)); fill<<<1024, 256>>>(p, tot, 1.0); }
   CK(cudaMalloc(&f, tot * 8)); fill<<<1024, 256>>>(f, tot, 0.1);
   CK(cudaMalloc(&coe, nn * 10 * 8)); fillcoe<<<256, 256>>>(coe, nn);
-  CK(cudaMalloc(&fac, nn * 2 * 8));
-  line_factor_kernel<double><<<dim3((nx / 8 + 63) / 64, ny), 64>>>(coe, fac, nx, ny);
+  CK(cudaMalloc(&fac, nn * kLineFacPlanes * 8));
+  line_factor_kernel<double><<<dim3((nx / 32 + 31) / 32 + 1, ny), 32>>>(coe, fac, nx, ny);
   const int tlx = (nx + ln::TW - 1) / ln::TW, tly = (ny + ln::TH - 1) / ln::TH;
   CK(cudaMalloc(&pack, (size_t)tlx * tly * kLinePlanes * ln::SEG * ln::NT * 8));
   line_pack_kernel<double><<<tlx * tly, ln::NT>>>(coe, fac, pack, nx, ny, tlx);

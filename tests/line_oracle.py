@@ -2,13 +2,13 @@
 
 The reference has no such method: the residual r = L psi - f is do_elliptic's nine-term sum
 (xtt-lib-fortran/elliptic_tools.f90:77-85) minus f, as in solve_elliptic (:189-190); the correction solves
-coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i) on segments of SEG radial points (global index aligned) instead of the
+coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i) on blocks of SEG radial points (global index aligned) instead of the
 reference's point-wise r / (-coe5) (:238).  Used to check the CUDA kernel sweep by sweep; the converged solution is
 checked against the reference algorithm itself in the tests.
 """
 import numpy as np
 
-SEG = 8
+SEG = 32     # block length of the relaxation (4 threads x 8 points in the CUDA kernel)
 _OFFS = [(-1, 1), (0, 1), (1, 1), (-1, 0), (0, 0), (1, 0), (-1, -1), (0, -1), (1, -1)]
 
 

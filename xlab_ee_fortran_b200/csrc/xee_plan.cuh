@@ -147,7 +147,7 @@ struct Plan : PlanBase {
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
   // v5 (segment-line relaxation, XEE_METHOD_LINE_*): Thomas factors, tiling, tensor-map cache
   bool use_line = false;
-  T* linefac = nullptr;              // [2][ny][nx]
+  T* linefac = nullptr;              // [6][ny][nx]: m, u, v, w, cB, cA (line_factor_kernel)
   T* linepack = nullptr;             // operator + factors in tile/thread order
   bool linefac_ready = false;
   int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
@@ -248,7 +248,7 @@ struct Plan : PlanBase {
         pool_free(partial); partial = nullptr;
         XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
       }
-      XEE_CHECK(pool_alloc(&linefac, sizeof(T) * 2 * nn));
+      XEE_CHECK(pool_alloc(&linefac, sizeof(T) * kLineFacPlanes * nn));
       XEE_CHECK(pool_alloc(&linepack, sizeof(T) * (size_t)nt * kLinePlanes * ln::SEG * ln::NT));
       want = 5;
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
@@ -391,8 +391,9 @@ struct Plan : PlanBase {
   }
   int line_factors() {   // Thomas factors of the radial segments (v5), once per operator
     if (!use_line) return 0;
-    dim3 g(((d.nx + ln::SEG - 1) / ln::SEG + 63) / 64, d.ny);
-    line_factor_kernel<T><<<g, 64, 0, own_stream>>>(coe, linefac, d.nx, d.ny);
+    const int nblk = (d.nx + ln::SEG * ln::BLK - 1) / (ln::SEG * ln::BLK);
+    dim3 g((nblk + 31) / 32, d.ny);
+    line_factor_kernel<T><<<g, 32, 0, own_stream>>>(coe, linefac, d.nx, d.ny);
     XEE_LAUNCH_OK();
     line_pack_kernel<T><<<ln_tiles_x * ln_tiles_y, ln::NT, 0, own_stream>>>(coe, linefac, linepack, d.nx, d.ny, ln_tiles_x);
     XEE_LAUNCH_OK();

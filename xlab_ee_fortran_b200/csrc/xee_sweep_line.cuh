@@ -1,27 +1,31 @@
-// xee_sweep_line.cuh — v5 sweep kernel for sm_100a: SEGMENT-LINE relaxation along the radius.
+// xee_sweep_line.cuh — v5 sweep kernel for sm_100a: BLOCK-LINE relaxation along the radius.
 //
 // Same discrete problem, same residual r = L psi - f (do_elliptic's nine-term sum, xtt-lib-fortran/
 // elliptic_tools.f90:77-85) and the same stop rule (:193-233) as solve_elliptic, but the correction is not the
-// reference's point-wise r / (-coe5) (:238): the radial line is cut into segments of 8 points and every segment's
-// tridiagonal system  coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i)  is solved exactly (Thomas algorithm, factors
-// precomputed once per operator), psi' = psi - alpha z.  On the secondary-circulation operator the radial coupling
-// carries ~97 % of the diagonal (dr >> dz after the 1/(rho r) scaling), so this block-Jacobi splitting has a 7x
-// larger spectral gap than point Jacobi and its Chebyshev acceleration needs ~2.6x fewer sweeps for the same
-// residual tolerance.  XEE_METHOD_LINE_JACOBI / XEE_METHOD_LINE_CHEBYSHEV; FAST arithmetic, shared operator.
+// reference's point-wise r / (-coe5) (:238): the radial line is cut into blocks of 32 points (global index aligned)
+// and every block's tridiagonal system  coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i)  is solved exactly,
+// psi' = psi - alpha z.  On the secondary-circulation operator the radial coupling carries ~97 % of the diagonal
+// (dr >> dz after the 1/(rho r) scaling), so this block-Jacobi splitting has a ~18x larger spectral gap than point
+// Jacobi and its Chebyshev acceleration needs ~4x fewer sweeps for the same residual tolerance.
+// XEE_METHOD_LINE_JACOBI / XEE_METHOD_LINE_CHEBYSHEV; FAST arithmetic, shared operator.
+//
+// The block solve is split over 4 threads of a warp (partitioned / SPIKE form, everything operator-dependent
+// precomputed once per operator by line_factor_kernel):
+//   * thread = 8 consecutive radial points of one row.  It solves its own 8-point segment with the Thomas algorithm
+//     in registers (z0 = M_t^-1 r), exchanges the two end values of z0 with the 3 other threads of the block by
+//     two butterfly shuffles, forms the true values of its neighbours' end points from 2 x 8 precomputed reduced-
+//     system coefficients, and subtracts the two precomputed spike vectors:  z = z0 - v b(t-1) - w a(t+1);
+//   * the 9 coefficients of its points (144 registers) and the 16 reduced coefficients stay in registers for the whole
+//     chunk of solves, the 4 x 8 factors (m, u, v, w) in thread-private shared-memory cells.
 //
 // Data movement (one sweep per pass, HBM-bound like the v2 kernel):
-//   * thread = 8 consecutive radial points of one row: the whole Thomas solve runs in its registers, with the
-//     9 coefficients of its points (144 registers) kept for the whole chunk of solves, the 2 Thomas factors in
-//     thread-private shared-memory cells;
-//   * warp = one segment column x 32 rows, lane = row.  TMA boxes are 70 (psi, with halo) and 66 (f, psi_{k-1})
-//     elements wide, i.e. an ODD number of 16-byte chunks per shared-memory row, so the 128-bit loads of the 32 lanes
-//     of a warp (same columns, consecutive rows) hit distinct banks without any swizzle;
+//   * warp = 32 columns x 8 rows (lane = segment-in-block * 8 + row).  TMA boxes are 70 (psi, with halo) and 66
+//     (f, psi_{k-1}) elements wide, i.e. an ODD number of 16-byte chunks per shared-memory row, so the 128-bit loads of
+//     8 lanes with the same columns and consecutive rows hit distinct banks without any swizzle;
 //   * one persistent CTA of 256 threads per SM, tiles of 64 x 32 points, 3-stage TMA ring, one named barrier per
 //     (tile, solve) to hand the stage back; results go to global memory as 128-bit stores;
 //   * the operator and the factors are repacked once per operator in tile/thread order (line_pack_kernel), so the
-//     per-unit reload of a thread's 88 constants is 44 fully coalesced 128-bit loads (2-3 us per unit instead of 10).
-// Measured on B200 (512 solves, 512x256, fp64, Chebyshev): 377 us per sweep = 5.66 TB/s algorithmic (87 % of the measured
-// copy peak); DRAM traffic 2.20 GB per sweep for 2.13 GB algorithmic.
+//     per-unit reload of a thread's constants is fully coalesced 128-bit loads (2-3 us per unit instead of 10).
 #pragma once
 #include <cuda.h>
 
@@ -32,7 +36,8 @@ namespace xee {
 enum { MODE_LINE_JACOBI = 3, MODE_LINE_CHEBYSHEV = 4 };
 
 namespace ln {
-constexpr int SEG = 8;             // points per thread = segment length of the line relaxation
+constexpr int SEG = 8;             // points per thread
+constexpr int BLK = 4;             // threads per block of the line relaxation: blocks of SEG * BLK = 32 radial points
 constexpr int TW = 64, TH = 32;    // tile (grid points)
 constexpr int NSEG = TW / SEG;     // 8 warps
 constexpr int NT = NSEG * TH;      // 256 threads
@@ -50,7 +55,7 @@ template <class T> struct Cfg {
   static constexpr int X_RAW = XP * (TH + 2), F_RAW = FP * TH;
   static constexpr int X_BYTES = (X_RAW + 127) / 128 * 128, F_BYTES = (F_RAW + 127) / 128 * 128;
   static constexpr int STAGE_BYTES = X_BYTES + 2 * F_BYTES;
-  static constexpr int FAC_BYTES = 2 * F_BYTES;     // the two Thomas-factor planes of the current tile (thread-private cells)
+  static constexpr int FAC_BYTES = 4 * F_BYTES;     // factor planes m, u, v, w of the current tile (thread-private cells)
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES;
   static_assert((XW / V) % 2 == 1 && (FW / V) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
@@ -93,44 +98,107 @@ template <class T> __device__ __forceinline__ void load_seg(uint32_t seg_addr, T
 #pragma unroll
   for (int q = 0; q < NV; ++q) lds16(seg_addr + 16u * q, &w[q * V]);
 }
+// thread -> (segment column, row) of the tile: warp = (32-column half, 8-row group), lane = segment-in-block * 8 + row,
+// so the 4 threads of a block sit in one warp (lanes l, l^8, l^16, l^24) and 8 consecutive lanes read consecutive rows.
+__device__ __forceinline__ int seg_of(int tid) { return ((tid >> 5) & 1) * BLK + ((tid >> 3) & 3); }
+__device__ __forceinline__ int row_of(int tid) { return (tid >> 6) * 8 + (tid & 7); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 }  // namespace ln
 
-// Thomas factors of every radial segment of a shared operator: fac[0] = m(i) = 1 / (coe5(i) - lo(i) u(i-1)),
-// fac[1] = u(i) = up(i) m(i), with lo = coe4 except at a segment start, up = coe6 except at a segment end; both 0 on
-// boundary points, which therefore get a zero correction.  One thread per (segment, row).
+// Everything the block solve needs from a shared operator, once per operator: fac[6][ny][nx] =
+//   0: m(i) = 1 / (coe5(i) - lo(i) u(i-1))   1: u(i) = up(i) m(i)      Thomas factors of the 8-point segments
+//      (lo = coe4 except at a segment start, up = coe6 except at a segment end; 0 on boundary points, which therefore
+//      get a zero correction),
+//   2: v = M_t^-1 (coe4(first) e_first)      3: w = M_t^-1 (coe6(last) e_last)      spike vectors of segment t,
+//   4: cB[k]   5: cA[k]   (8 values per segment)  rows of the inverse of the 8 x 8 reduced system that give b(t-1), the
+//      true last value of the segment to the left, and a(t+1), the true first value of the segment to the right, from
+//      the end values of the four local solutions in the order a thread holds them after the two butterfly exchanges:
+//      [own first, own last, those of t^1, of t^2, of t^3].
+// One thread per (block of 32 points, row).
 template <class T>
 __global__ void line_factor_kernel(const T* __restrict__ coe, T* __restrict__ fac, int nx, int ny) {
-  const int sgi = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  const int i0 = sgi * ln::SEG;
-  if (i0 >= nx) return;
+  constexpr int S = ln::SEG, B = ln::BLK, NB = S * B;
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  const int ib = blk * NB;
+  if (ib >= nx) return;
   const size_t nn = (size_t)nx * ny;
-  T u_prev = T(0);
-  for (int e = 0; e < ln::SEG && i0 + e < nx; ++e) {
-    const int i = i0 + e;
-    const size_t o = (size_t)j * nx + i;
-    const bool interior = i > 0 && i < nx - 1 && j > 0 && j < ny - 1;
-    T m = T(0), u = T(0);
-    if (interior) {
-      const T lo = e == 0 ? T(0) : coe[3 * nn + o];
-      const T up = e == ln::SEG - 1 ? T(0) : coe[5 * nn + o];
-      m = T(1) / (coe[4 * nn + o] - lo * u_prev);
-      u = up * m;
+  T m[NB], u[NB], v[NB], w[NB];
+  for (int t = 0; t < B; ++t) {
+    T c4f = T(0), c6l = T(0);
+    T u_prev = T(0);
+    for (int e = 0; e < S; ++e) {
+      const int q = t * S + e, i = ib + q;
+      const bool interior = i > 0 && i < nx - 1 && j > 0 && j < ny - 1;
+      m[q] = T(0); u[q] = T(0);
+      if (interior) {
+        const size_t o = (size_t)j * nx + i;
+        const T lo = e == 0 ? T(0) : coe[3 * nn + o];
+        const T up = e == S - 1 ? T(0) : coe[5 * nn + o];
+        m[q] = T(1) / (coe[4 * nn + o] - lo * u_prev);
+        u[q] = up * m[q];
+        if (e == 0 && t > 0) c4f = coe[3 * nn + o];
+        if (e == S - 1 && t < B - 1) c6l = coe[5 * nn + o];
+      }
+      u_prev = u[q];
     }
-    fac[o] = m; fac[nn + o] = u;
-    u_prev = u;
+    // spikes: the same forward / backward recurrences as the sweep kernel, right-hand sides c4f e_0 and c6l e_{S-1}
+    T y = T(0);
+    for (int e = 0; e < S; ++e) {
+      const int q = t * S + e, i = ib + q;
+      const T c4 = (e > 0 && i < nx && m[q] != T(0)) ? coe[3 * nn + (size_t)j * nx + i] : T(0);
+      y = ((e == 0 ? c4f : T(0)) - c4 * y) * m[q];
+      v[q] = y;
+    }
+    for (int e = S - 2; e >= 0; --e) v[t * S + e] -= u[t * S + e] * v[t * S + e + 1];
+    for (int e = 0; e < S; ++e) w[t * S + e] = T(0);
+    w[t * S + S - 1] = c6l * m[t * S + S - 1];
+    for (int e = S - 2; e >= 0; --e) w[t * S + e] = -u[t * S + e] * w[t * S + e + 1];
+  }
+  // reduced system R (a_0, b_0, a_1, b_1, ...) = (first, last of the local solutions), then its inverse (Gauss-Jordan;
+  // R = I + off-diagonal entries of magnitude < 1 for a diagonally dominant operator)
+  constexpr int NR = 2 * B;
+  double R[NR][NR], Ri[NR][NR];
+  for (int p = 0; p < NR; ++p)
+    for (int q = 0; q < NR; ++q) { R[p][q] = p == q ? 1.0 : 0.0; Ri[p][q] = p == q ? 1.0 : 0.0; }
+  for (int t = 0; t < B; ++t) {
+    if (t > 0) { R[2 * t][2 * (t - 1) + 1] = (double)v[t * S]; R[2 * t + 1][2 * (t - 1) + 1] = (double)v[t * S + S - 1]; }
+    if (t < B - 1) { R[2 * t][2 * (t + 1)] = (double)w[t * S]; R[2 * t + 1][2 * (t + 1)] = (double)w[t * S + S - 1]; }
+  }
+  for (int p = 0; p < NR; ++p) {
+    const double piv = 1.0 / R[p][p];
+    for (int q = 0; q < NR; ++q) { R[p][q] *= piv; Ri[p][q] *= piv; }
+    for (int o = 0; o < NR; ++o) {
+      if (o == p) continue;
+      const double fct = R[o][p];
+      if (fct == 0.0) continue;
+      for (int q = 0; q < NR; ++q) { R[o][q] -= fct * R[p][q]; Ri[o][q] -= fct * Ri[p][q]; }
+    }
+  }
+  for (int t = 0; t < B; ++t) {
+    for (int e = 0; e < S; ++e) {
+      const int q = t * S + e, i = ib + q;
+      if (i >= nx) continue;
+      const size_t o = (size_t)j * nx + i;
+      fac[o] = m[q]; fac[nn + o] = u[q]; fac[2 * nn + o] = v[q]; fac[3 * nn + o] = w[q];
+      const int src = t ^ (e >> 1), col = 2 * src + (e & 1);        // gathered order: own, t^1, t^2, t^3
+      fac[4 * nn + o] = t > 0 ? (T)Ri[2 * (t - 1) + 1][col] : T(0);
+      fac[5 * nn + o] = t < B - 1 ? (T)Ri[2 * (t + 1)][col] : T(0);
+    }
   }
 }
 
 // Operator + factors repacked per tile in the order the sweep kernel's threads read them:
-// pack[tile][plane 0..10][chunk q][thread][V] (planes 0..8 = coe1..coe9, 9 = m, 10 = u), zeros outside the field.  A warp's
+// pack[tile][plane 0..14][chunk q][thread][V] (planes 0..8 = coe1..coe9, 9..14 = the factor planes), zeros outside the field.  A warp's
 // 128-bit load of (plane, chunk) is then one contiguous 512-byte run instead of 32 rows 4 KB apart.
-constexpr int kLinePlanes = 11;
+constexpr int kLinePlanes = 15;
+constexpr int kLineFacPlanes = 6;
 template <class T>
 __global__ void __launch_bounds__(ln::NT) line_pack_kernel(const T* __restrict__ coe, const T* __restrict__ fac,
                                                            T* __restrict__ pack, int nx, int ny, int tiles_x) {
   using C = ln::Cfg<T>;
   const int tile = blockIdx.x, tid = threadIdx.x;
-  const int sg = tid >> 5, r = tid & 31;
+  const int sg = ln::seg_of(tid), r = ln::row_of(tid);
   const int gi = (tile % tiles_x) * ln::TW + ln::SEG * sg, gj = (tile / tiles_x) * ln::TH + r;
   const size_t nn = (size_t)nx * ny;
   T* out = pack + (size_t)tile * kLinePlanes * ln::SEG * ln::NT;
@@ -207,8 +275,8 @@ __global__ void __launch_bounds__(ln::NT, 1)
     for (int q = 0; q < NSTAGE; ++q)
       if (!issue_next()) break;
 
-  const int sg = tid >> 5;          // warp = segment column of the tile
-  const int r = tid & 31;           // lane = row of the tile
+  const int sg = seg_of(tid);       // segment column of the tile (0..7)
+  const int r = row_of(tid);        // row of the tile (0..31)
   const uint32_t sm0 = tma::smem_u32(smem_raw);
   const uint32_t xofs = (uint32_t)((r + 1) * C::XP + (V + SEG * sg) * C::ES);   // own segment in the psi box
   const uint32_t fofs = (uint32_t)(C::X_BYTES + r * C::FP + SEG * sg * C::ES);  // ... in the f box
@@ -227,9 +295,9 @@ __global__ void __launch_bounds__(ln::NT, 1)
 #pragma unroll
     for (int e = 0; e < SEG; ++e)
       if (gi + e >= 1 && gi + e < a.nx - 1 && gj >= 1 && gj < a.ny - 1) inb |= 1u << e;
-    // the 9 coefficients of the thread's points stay in registers for the whole chunk; its 2 x 8 Thomas factors go to
-    // thread-private cells of shared memory (read back by the same thread only: no barrier needed)
-    T cf[9][SEG];
+    // the 9 coefficients of the thread's points and its 2 x 8 reduced-system coefficients stay in registers for the whole
+    // chunk; the factors m, u, v, w go to thread-private cells of shared memory (read back by the same thread only)
+    T cf[9][SEG], cB[SEG], cA[SEG];
     {
       const T* pk = a.pack + ((size_t)tile * kLinePlanes * SEG * NT + (size_t)tid * V);
 #pragma unroll
@@ -237,10 +305,16 @@ __global__ void __launch_bounds__(ln::NT, 1)
 #pragma unroll
         for (int q = 0; q < NV; ++q) ldg16(pk + (size_t)(k * NV + q) * NT * V, &cf[k][q * V]);
 #pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          T t[V];
+          ldg16(pk + (size_t)((9 + k) * NV + q) * NT * V, t); sts16(faca + k * C::F_BYTES + 16u * q, t);
+        }
+#pragma unroll
       for (int q = 0; q < NV; ++q) {
-        T t[V];
-        ldg16(pk + (size_t)(9 * NV + q) * NT * V, t); sts16(faca + 16u * q, t);
-        ldg16(pk + (size_t)(10 * NV + q) * NT * V, t); sts16(faca + C::F_BYTES + 16u * q, t);
+        ldg16(pk + (size_t)(13 * NV + q) * NT * V, &cB[q * V]);
+        ldg16(pk + (size_t)(14 * NV + q) * NT * V, &cA[q * V]);
       }
     }
     for (int n = n0; n < n1; ++n) {
@@ -300,6 +374,25 @@ __global__ void __launch_bounds__(ln::NT, 1)
         load_seg<T>(faca + C::F_BYTES, uf);
 #pragma unroll
         for (int e = SEG - 2; e >= 0; --e) acc[e] = Rn<T>::fma(-uf[e], acc[e + 1], acc[e]);
+      }
+      // ---- couple the 4 segments of the 32-point block: end values of the local solutions around the block (two
+      // butterfly exchanges), true neighbour end values from the reduced system, minus the spikes
+      {
+        T g[2 * BLK];
+        g[0] = acc[0]; g[1] = acc[SEG - 1];
+        g[2] = shfl_xor(g[0], 8); g[3] = shfl_xor(g[1], 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[4 + k] = shfl_xor(g[k], 16);
+        T bl = cB[0] * g[0], ar = cA[0] * g[0];
+#pragma unroll
+        for (int k = 1; k < 2 * BLK; ++k) { bl = Rn<T>::fma(cB[k], g[k], bl); ar = Rn<T>::fma(cA[k], g[k], ar); }
+        T vf[SEG];
+        load_seg<T>(faca + 2 * C::F_BYTES, vf);
+#pragma unroll
+        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-vf[e], bl, acc[e]);
+        load_seg<T>(faca + 3 * C::F_BYTES, vf);
+#pragma unroll
+        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-vf[e], ar, acc[e]);
       }
       // ---- update
       T out[SEG];
