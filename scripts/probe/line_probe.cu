@@ -26,14 +26,14 @@ int main(int argc, char** argv) {
   void* fp = nullptr; cudaDriverEntryPointQueryResult q;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q)); enc = (Enc)fp;
   const size_t nn = (size_t)nx * ny, tot = nn * nb;
-  double *x[2], *f, *coe, *fac, *pack;
+  double *x[2], *f, *coe, *fac; unsigned char* pack;
   for (auto& p : x) { CK(cudaMalloc(&p, tot * 8)); fill<<<1024, 256>>>(p, tot, 1.0); }
   CK(cudaMalloc(&f, tot * 8)); fill<<<1024, 256>>>(f, tot, 0.1);
   CK(cudaMalloc(&coe, nn * 10 * 8)); fillcoe<<<256, 256>>>(coe, nn);
   CK(cudaMalloc(&fac, nn * kLineFacPlanes * 8));
   line_factor_kernel<double><<<dim3((nx / 32 + 31) / 32 + 1, ny), 32>>>(coe, fac, nx, ny);
   const int tlx = (nx + ln::TW - 1) / ln::TW, tly = (ny + ln::TH - 1) / ln::TH;
-  CK(cudaMalloc(&pack, (size_t)tlx * tly * kLinePlanes * ln::SEG * ln::NT * 8));
+  CK(cudaMalloc(&pack, (size_t)tlx * tly * line_pack_tile_bytes<double>()));
   line_pack_kernel<double><<<tlx * tly, ln::NT>>>(coe, fac, pack, nx, ny, tlx);
   CUtensorMap mxh[2], mxp[2];
   for (int k = 0; k < 2; ++k) { mxh[k] = mk(x[k], nx, ny, nb, ln::Cfg<double>::XW, ln::TH + 2); mxp[k] = mk(x[k], nx, ny, nb, ln::Cfg<double>::FW, ln::TH); }

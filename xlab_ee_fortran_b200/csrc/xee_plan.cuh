@@ -148,7 +148,7 @@ struct Plan : PlanBase {
   // v5 (segment-line relaxation, XEE_METHOD_LINE_*): Thomas factors, tiling, tensor-map cache
   bool use_line = false;
   T* linefac = nullptr;              // [6][ny][nx]: m, u, v, w, cB, cA (line_factor_kernel)
-  T* linepack = nullptr;             // operator + factors in tile/thread order
+  unsigned char* linepack = nullptr; // operator + factors in tile/thread order
   bool linefac_ready = false;
   int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
   struct LineMap { const void* ptr; int nb; int kind; CUtensorMap map; };
@@ -249,7 +249,7 @@ struct Plan : PlanBase {
         XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
       }
       XEE_CHECK(pool_alloc(&linefac, sizeof(T) * kLineFacPlanes * nn));
-      XEE_CHECK(pool_alloc(&linepack, sizeof(T) * (size_t)nt * kLinePlanes * ln::SEG * ln::NT));
+      XEE_CHECK(pool_alloc(&linepack, (size_t)nt * line_pack_tile_bytes<T>()));
       want = 5;
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true

@@ -16,7 +16,11 @@
 //     two butterfly shuffles, forms the true values of its neighbours' end points from 2 x 8 precomputed reduced-
 //     system coefficients, and subtracts the two precomputed spike vectors:  z = z0 - v b(t-1) - w a(t+1);
 //   * the 9 coefficients of its points (144 registers) and the 16 reduced coefficients stay in registers for the whole
-//     chunk of solves, the 4 x 8 factors (m, u, v, w) in thread-private shared-memory cells.
+//     chunk of solves, the 4 x 8 factors (m, u, v, w) in thread-private shared-memory cells.  The coupling data (v, w
+//     and the reduced coefficients) are stored in FLOAT: the local Thomas solve is exact in working precision, the
+//     coupling correction carries a 6e-8 relative perturbation.  That only perturbs the (fixed, linear) approximate
+//     inverse that multiplies the residual — the fixed point L psi = f and the residual-based stop rule are untouched —
+//     and it halves the shared-memory traffic and the registers of the coupling step.
 //
 // Data movement (one sweep per pass, HBM-bound like the v2 kernel):
 //   * warp = 32 columns x 8 rows (lane = segment-in-block * 8 + row).  TMA boxes are 70 (psi, with halo) and 66
@@ -55,7 +59,10 @@ template <class T> struct Cfg {
   static constexpr int X_RAW = XP * (TH + 2), F_RAW = FP * TH;
   static constexpr int X_BYTES = (X_RAW + 127) / 128 * 128, F_BYTES = (F_RAW + 127) / 128 * 128;
   static constexpr int STAGE_BYTES = X_BYTES + 2 * F_BYTES;
-  static constexpr int FAC_BYTES = 4 * F_BYTES;     // factor planes m, u, v, w of the current tile (thread-private cells)
+  // thread-private cells of the current tile's factor planes: m, u in working precision (pitch FP), the spikes v, w in
+  // float (8 floats = 2 chunks per thread, pitch AP = 17 chunks)
+  static constexpr int AP = (TW + 4) * 4, A_BYTES = AP * TH;
+  static constexpr int FAC_BYTES = 2 * F_BYTES + 2 * A_BYTES;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES;
   static_assert((XW / V) % 2 == 1 && (FW / V) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
@@ -111,6 +118,7 @@ __device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sy
 //      (lo = coe4 except at a segment start, up = coe6 except at a segment end; 0 on boundary points, which therefore
 //      get a zero correction),
 //   2: v = M_t^-1 (coe4(first) e_first)      3: w = M_t^-1 (coe6(last) e_last)      spike vectors of segment t,
+//   (planes 2..5 hold float-representable values: the sweep kernel keeps them in float)
 //   4: cB[k]   5: cA[k]   (8 values per segment)  rows of the inverse of the 8 x 8 reduced system that give b(t-1), the
 //      true last value of the segment to the left, and a(t+1), the true first value of the segment to the right, from
 //      the end values of the four local solutions in the order a thread holds them after the two butterfly exchanges:
@@ -180,40 +188,47 @@ __global__ void line_factor_kernel(const T* __restrict__ coe, T* __restrict__ fa
       const int q = t * S + e, i = ib + q;
       if (i >= nx) continue;
       const size_t o = (size_t)j * nx + i;
-      fac[o] = m[q]; fac[nn + o] = u[q]; fac[2 * nn + o] = v[q]; fac[3 * nn + o] = w[q];
+      fac[o] = m[q]; fac[nn + o] = u[q]; fac[2 * nn + o] = (T)(float)v[q]; fac[3 * nn + o] = (T)(float)w[q];
       const int src = t ^ (e >> 1), col = 2 * src + (e & 1);        // gathered order: own, t^1, t^2, t^3
-      fac[4 * nn + o] = t > 0 ? (T)Ri[2 * (t - 1) + 1][col] : T(0);
-      fac[5 * nn + o] = t < B - 1 ? (T)Ri[2 * (t + 1)][col] : T(0);
+      fac[4 * nn + o] = t > 0 ? (T)(float)Ri[2 * (t - 1) + 1][col] : T(0);
+      fac[5 * nn + o] = t < B - 1 ? (T)(float)Ri[2 * (t + 1)][col] : T(0);
     }
   }
 }
 
-// Operator + factors repacked per tile in the order the sweep kernel's threads read them:
-// pack[tile][plane 0..14][chunk q][thread][V] (planes 0..8 = coe1..coe9, 9..14 = the factor planes), zeros outside the field.  A warp's
-// 128-bit load of (plane, chunk) is then one contiguous 512-byte run instead of 32 rows 4 KB apart.
-constexpr int kLinePlanes = 15;
+// Operator + factors repacked per tile in the order the sweep kernel's threads read them: 11 planes in working precision
+// pack[tile][plane 0..10][chunk q][thread][V] (coe1..coe9, m, u), then 4 float planes [plane][chunk 0..1][thread][4]
+// (v, w, cB, cA); zeros outside the field.  A warp's 128-bit load of (plane, chunk) is one contiguous 512-byte run
+// instead of 32 rows 4 KB apart.
 constexpr int kLineFacPlanes = 6;
+template <class T> __host__ __device__ constexpr size_t line_pack_tile_bytes() {
+  return (size_t)(11 * ln::Cfg<T>::NV + 4 * 2) * ln::NT * 16;
+}
 template <class T>
 __global__ void __launch_bounds__(ln::NT) line_pack_kernel(const T* __restrict__ coe, const T* __restrict__ fac,
-                                                           T* __restrict__ pack, int nx, int ny, int tiles_x) {
+                                                           unsigned char* __restrict__ pack, int nx, int ny, int tiles_x) {
   using C = ln::Cfg<T>;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int sg = ln::seg_of(tid), r = ln::row_of(tid);
   const int gi = (tile % tiles_x) * ln::TW + ln::SEG * sg, gj = (tile / tiles_x) * ln::TH + r;
   const size_t nn = (size_t)nx * ny;
-  T* out = pack + (size_t)tile * kLinePlanes * ln::SEG * ln::NT;
-  for (int k = 0; k < kLinePlanes; ++k) {
+  unsigned char* base = pack + (size_t)tile * line_pack_tile_bytes<T>();
+  T* out = reinterpret_cast<T*>(base);
+  float* aux = reinterpret_cast<float*>(base + (size_t)11 * C::NV * ln::NT * 16);
+  for (int k = 0; k < 15; ++k) {
     const T* src = k < 9 ? coe + k * nn : fac + (k - 9) * nn;
     for (int e = 0; e < ln::SEG; ++e) {
       const bool in = gj < ny && gi + e < nx;
-      out[((size_t)(k * C::NV + e / C::V) * ln::NT + tid) * C::V + e % C::V] = in ? src[(size_t)gj * nx + gi + e] : T(0);
+      const T val = in ? src[(size_t)gj * nx + gi + e] : T(0);
+      if (k < 11) out[((size_t)(k * C::NV + e / C::V) * ln::NT + tid) * C::V + e % C::V] = val;
+      else aux[((size_t)((k - 11) * 2 + e / 4) * ln::NT + tid) * 4 + e % 4] = (float)val;
     }
   }
 }
 
 template <class T>
 struct LineArgs {
-  const T* pack;           // operator + Thomas factors in tile/thread order (line_pack_kernel)
+  const unsigned char* pack;   // operator + factors in tile/thread order (line_pack_kernel)
   T* dst;                  // psi_{k+1} (holds psi_{k-1} on entry: read through map_xm at the own cells only)
   long long field_stride;  // nx*ny
   int nx, ny, nbatch;
@@ -280,7 +295,8 @@ __global__ void __launch_bounds__(ln::NT, 1)
   const uint32_t sm0 = tma::smem_u32(smem_raw);
   const uint32_t xofs = (uint32_t)((r + 1) * C::XP + (V + SEG * sg) * C::ES);   // own segment in the psi box
   const uint32_t fofs = (uint32_t)(C::X_BYTES + r * C::FP + SEG * sg * C::ES);  // ... in the f box
-  const uint32_t faca = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + r * C::FP + SEG * sg * C::ES);   // own cells of the factor planes
+  const uint32_t faca = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + r * C::FP + SEG * sg * C::ES);   // own cells of the factor planes m, u
+  const uint32_t auxa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + 2 * C::F_BYTES + r * C::AP + SEG * sg * 4);   // ... v, w (float)
   uint32_t it = 0;
 
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -295,26 +311,36 @@ __global__ void __launch_bounds__(ln::NT, 1)
 #pragma unroll
     for (int e = 0; e < SEG; ++e)
       if (gi + e >= 1 && gi + e < a.nx - 1 && gj >= 1 && gj < a.ny - 1) inb |= 1u << e;
-    // the 9 coefficients of the thread's points and its 2 x 8 reduced-system coefficients stay in registers for the whole
-    // chunk; the factors m, u, v, w go to thread-private cells of shared memory (read back by the same thread only)
-    T cf[9][SEG], cB[SEG], cA[SEG];
+    // the 9 coefficients of the thread's points and its 2 x 8 reduced-system coefficients (float) stay in registers for the
+    // whole chunk; the factors m, u, v, w go to thread-private cells of shared memory (read back by the same thread only)
+    T cf[9][SEG];
+    float cB[SEG], cA[SEG];
     {
-      const T* pk = a.pack + ((size_t)tile * kLinePlanes * SEG * NT + (size_t)tid * V);
+      const unsigned char* pb = a.pack + (size_t)tile * line_pack_tile_bytes<T>();
+      const T* pk = reinterpret_cast<const T*>(pb) + (size_t)tid * V;
+      const float* pa = reinterpret_cast<const float*>(pb + (size_t)11 * NV * NT * 16) + (size_t)tid * 4;
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
         for (int q = 0; q < NV; ++q) ldg16(pk + (size_t)(k * NV + q) * NT * V, &cf[k][q * V]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 2; ++k)
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
           T t[V];
           ldg16(pk + (size_t)((9 + k) * NV + q) * NT * V, t); sts16(faca + k * C::F_BYTES + 16u * q, t);
         }
 #pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        ldg16(pk + (size_t)(13 * NV + q) * NT * V, &cB[q * V]);
-        ldg16(pk + (size_t)(14 * NV + q) * NT * V, &cA[q * V]);
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float t[4];
+          ldg16(pa + (size_t)(k * 2 + q) * NT * 4, t); sts16(auxa + k * C::A_BYTES + 16u * q, t);
+        }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        ldg16(pa + (size_t)(4 + q) * NT * 4, &cB[q * 4]);
+        ldg16(pa + (size_t)(6 + q) * NT * 4, &cA[q * 4]);
       }
     }
     for (int n = n0; n < n1; ++n) {
@@ -383,16 +409,16 @@ __global__ void __launch_bounds__(ln::NT, 1)
         g[2] = shfl_xor(g[0], 8); g[3] = shfl_xor(g[1], 8);
 #pragma unroll
         for (int k = 0; k < 4; ++k) g[4 + k] = shfl_xor(g[k], 16);
-        T bl = cB[0] * g[0], ar = cA[0] * g[0];
+        T bl = (T)cB[0] * g[0], ar = (T)cA[0] * g[0];
 #pragma unroll
-        for (int k = 1; k < 2 * BLK; ++k) { bl = Rn<T>::fma(cB[k], g[k], bl); ar = Rn<T>::fma(cA[k], g[k], ar); }
-        T vf[SEG];
-        load_seg<T>(faca + 2 * C::F_BYTES, vf);
+        for (int k = 1; k < 2 * BLK; ++k) { bl = Rn<T>::fma((T)cB[k], g[k], bl); ar = Rn<T>::fma((T)cA[k], g[k], ar); }
+        float vf[SEG];
+        lds16(auxa, &vf[0]); lds16(auxa + 16u, &vf[4]);
 #pragma unroll
-        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-vf[e], bl, acc[e]);
-        load_seg<T>(faca + 3 * C::F_BYTES, vf);
+        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-(T)vf[e], bl, acc[e]);
+        lds16(auxa + C::A_BYTES, &vf[0]); lds16(auxa + C::A_BYTES + 16u, &vf[4]);
 #pragma unroll
-        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-vf[e], ar, acc[e]);
+        for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(-(T)vf[e], ar, acc[e]);
       }
       // ---- update
       T out[SEG];
