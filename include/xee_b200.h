@@ -56,7 +56,7 @@ void xee_do_elliptic_f64(const double* psi, const double* coe, double* outdat, c
  * hit).  Both criteria non-positive: prints the reference's message and stops the
  * process like Fortran STOP (exit status 0), elliptic_tools.f90:126-129.
  * Environment: XEE_ARITH=strict|fast (default strict: no FMA contraction, true division,
- * iterates bit-identical to the reference's operation order); XEE_METHOD=jacobi|chebyshev
+ * iterates bit-identical to the reference's operation order); XEE_METHOD=jacobi|chebyshev|line_jacobi|line_chebyshev
  * (default jacobi, the reference's iteration). */
 void xee_solve_elliptic_f32(int* max_iter, const int* check_step, const int* converge_time, const int* lost_rate,
                             float* strategy_r1, float* strategy_r2, const float* alpha, float* dat,
