@@ -177,13 +177,19 @@ __global__ void __launch_bounds__(tb::NT, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NSTAGE];
   __shared__ double red[NT / 32];
+  __shared__ uint32_t sdone[kDoneWords];   // stop flags of the batch as a bit mask: no global load per (tile, solve)
 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const bool done_in_smem = stage_done_flags(a.done, a.nbatch, sdone, tid, NT);
   __syncthreads();
+  auto is_done = [&](int n) -> bool {
+    if (a.done == nullptr) return false;
+    return done_in_smem ? ((sdone[n >> 5] >> (n & 31)) & 1u) != 0u : a.done[n] != 0;
+  };
 
   const int ntiles = a.tiles_x * a.tiles_y;
   const int nunits = ntiles * a.nchunks;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(tb::NT, 1)
       const int n0 = ch * a.chunk, n1 = min(n0 + a.chunk, a.nbatch);
       if (pn < 0) pn = n0; else ++pn;
       if (pn >= n1) { pu += gridDim.x; pn = -1; continue; }
-      if (a.done != nullptr && a.done[pn]) continue;
+      if (is_done(pn)) continue;
       const int tile = pu % ntiles;
       const int ox = (tile % a.tiles_x) * step_x, oy = (tile / a.tiles_x) * step_y;
       const int s = issued % NSTAGE;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(tb::NT, 1)
     }
     const long long gofs = (long long)(oy + r0) * a.nx + gi;      // the thread's first cell inside a field
     for (int n = n0; n < n1; ++n) {
-      if (a.done != nullptr && a.done[n]) continue;
+      if (is_done(n)) continue;
       const uint32_t s = it % NSTAGE;
       mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
       const uint32_t sb = sm0 + C::STAGE0 + s * C::STAGE_BYTES;    // psi_k | f | psi_{k-1} of this item

@@ -76,6 +76,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 }  // namespace tma
 
+// Per-solve stop flags -> bit mask in shared memory (warp ballots), so that the persistent kernels test a flag per
+// (tile, solve) without a dependent global load.  Returns false (nothing staged) when there are no flags or the batch
+// is larger than the mask; the caller must __syncthreads() before reading.
+constexpr int kDoneWords = 512;
+__device__ __forceinline__ bool stage_done_flags(const int* done, int nbatch, uint32_t* sdone, int tid, int nthreads) {
+  if (done == nullptr || nbatch > kDoneWords * 32) return false;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  for (int w = warp; w * 32 < nbatch; w += nwarps) {
+    const int n = w * 32 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, n < nbatch ? done[n] != 0 : true);
+    if (lane == 0) sdone[w] = m;
+  }
+  return true;
+}
+
 template <class T>
 struct TmaSweepArgs {
   SweepArgs<T> a;
