@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
   A.tiles_x = (nx + ln::TW - 1) / ln::TW; A.tiles_y = (ny + ln::TH - 1) / ln::TH;
   A.chunk = chunk; A.nchunks = (nb + chunk - 1) / chunk;
   const long long units = (long long)A.tiles_x * A.tiles_y * A.nchunks;
-  const int grid = (int)std::min<long long>(sms, units);
+  const int grid = (int)std::min<long long>((long long)sms * ln::CTAS_PER_SM, units);
   auto kern = sweep_line_kernel<double, true, false>;
   const int smem = ln::Cfg<double>::SMEM_BYTES;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

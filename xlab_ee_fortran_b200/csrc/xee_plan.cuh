@@ -498,7 +498,7 @@ struct Plan : PlanBase {
     A.alpha = a.alpha; A.omega = a.omega; A.rho_ps = a.rho_ps; A.cheb_k = a.cheb_k; A.done = a.done; A.partial = partial;
     A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
-    const int grid = (int)std::min<long long>(num_sms, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
+    const int grid = (int)std::min<long long>((long long)num_sms * ln::CTAS_PER_SM, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
     int rc;
     if (mode == MODE_CHEBYSHEV) rc = check ? launch_line_inst<true, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<true, false>(A, grid, cx, cxm, cf, s);
     else rc = check ? launch_line_inst<false, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<false, false>(A, grid, cx, cxm, cf, s);

@@ -42,7 +42,11 @@ enum { MODE_LINE_JACOBI = 3, MODE_LINE_CHEBYSHEV = 4 };
 namespace ln {
 constexpr int SEG = 8;             // points per thread
 constexpr int BLK = 4;             // threads per block of the line relaxation: blocks of SEG * BLK = 32 radial points
-constexpr int TW = 64, TH = 32;    // tile (grid points)
+#ifndef XEE_LINE_TH
+#define XEE_LINE_TH 32
+#endif
+constexpr int TW = 64, TH = XEE_LINE_TH;    // tile (grid points); TH = 16 runs two CTAs of 128 threads per SM
+constexpr int CTAS_PER_SM = 32 / TH;
 constexpr int NSEG = TW / SEG;     // 8 warps
 constexpr int NT = NSEG * TH;      // 256 threads
 #ifndef XEE_LINE_NSTAGE
@@ -241,7 +245,7 @@ struct LineArgs {
 };
 
 template <class T, bool CHEB, bool CHECK>
-__global__ void __launch_bounds__(ln::NT, 1)
+__global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
     sweep_line_kernel(const __grid_constant__ LineArgs<T> a, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_xm, const __grid_constant__ CUtensorMap map_f) {
   using namespace ln;
