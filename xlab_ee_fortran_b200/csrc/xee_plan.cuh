@@ -443,7 +443,10 @@ struct Plan : PlanBase {
     const size_t smem = (size_t)stage * P.nstage;
     static bool attr_done = false;
     if (!attr_done) {
-      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      cudaFuncAttributes fa{};
+      XEE_CHECK(cudaFuncGetAttributes(&fa, sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>));
+      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes));
       attr_done = true;
     }
     sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE><<<tma_grid, tma::NTHREADS, smem, s>>>(P, ms, mp, map_f, map_coe);

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NSTAGE_MAX], empty_bar[NSTAGE_MAX];
   __shared__ double red[NCONS / 32];
+  __shared__ uint32_t sdone[kDoneWords];   // stop flags of the batch as a bit mask: no global load per (tile, solve)
 
   const SweepArgs<T>& a = P.a;
   const int tid = threadIdx.x;
@@ -123,7 +124,12 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
     for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCONS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const bool done_in_smem = stage_done_flags(a.done, a.nbatch, sdone, tid, NTHREADS);
   __syncthreads();
+  auto is_done = [&](int n) -> bool {
+    if (a.done == nullptr) return false;
+    return done_in_smem ? ((sdone[n >> 5] >> (n & 31)) & 1u) != 0u : a.done[n] != 0;
+  };
 
   const int ntiles = P.tiles_x * P.tiles_y;
   const int nunits = ntiles * P.nchunks;
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
         const int i0 = 1 + (tile % P.tiles_x) * TW, j0 = 1 + (tile / P.tiles_x) * TH;
         const int n0 = ch * P.chunk, n1 = min(n0 + P.chunk, a.nbatch);
         for (int n = n0; n < n1; ++n) {
-          if (a.done != nullptr && a.done[n]) continue;
+          if (is_done(n)) continue;
           const int s = it % nstage;
           const uint32_t ph = (it / nstage) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 1)
       }
     }
     for (int n = n0; n < n1; ++n) {
-      if (a.done != nullptr && a.done[n]) continue;
+      if (is_done(n)) continue;
       const int s = it % nstage;
       const uint32_t ph = (it / nstage) & 1;
       mbar_wait(&full_bar[s], ph);
