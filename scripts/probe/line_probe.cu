@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
   CUtensorMap mf = mk(f, nx, ny, nb, ln::Cfg<double>::FW, ln::TH);
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   LineArgs<double> A{};
-  A.pack = pack; A.field_stride = (long long)nn; A.nx = nx; A.ny = ny; A.nbatch = nb; A.alpha = 1.0; A.omega = 1.2;
+  A.pack = pack; A.pack_set_stride = 0; A.field_stride = (long long)nn; A.nx = nx; A.ny = ny; A.nbatch = nb; A.alpha = 1.0; A.omega = 1.2;
   A.tiles_x = (nx + ln::TW - 1) / ln::TW; A.tiles_y = (ny + ln::TH - 1) / ln::TH;
   A.chunk = chunk; A.nchunks = (nb + chunk - 1) / chunk;
   const long long units = (long long)A.tiles_x * A.tiles_y * A.nchunks;

@@ -70,13 +70,14 @@ if 3 in which:   # map: 64x32 heating-location sweep on 256x128, one GPU
 if 5 in which:   # time series: 128 of the 1024 snapshots (one GPU's share of 8) on 512x256, one operator per snapshot
     nr, nz, ns = 512, 256, 128
     params = W.series_params(ns, total=1024, first=0)
-    ts = TimeSeries(nr, nz, Lr, Lz, ns, "f64", arith="fast", method="chebyshev", r1_rel=1e-12)
-    prm = X.SolveParams(max_iter=2000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=2, stall_checks=20)
+    ts = TimeSeries(nr, nz, Lr, Lz, ns, "f64", arith="fast", method=ACC, r1_rel=1e-12)
+    prm = X.SolveParams(max_iter=2000000, check_step=CS, converge_time=2, r1=1.0, r2=0.0, sync_every=2, stall_checks=20)
     ts.run(params, prm); ts.sweep_kernel_stats(reset=True)
     t = time.time(); tab = ts.run(params, prm); dt = time.time() - t
     ms, n = ts.sweep_kernel_stats()
     pts = (nr - 2) * (nz - 2)
-    alg = float(tab[:, 0].sum()) * pts * 8 * 13     # psi r/w, psi_{k-1}, f, 9 coefficients
+    # psi r/w, psi_{k-1}, f, 9 coefficients (+ 2 factors in working precision and 4 float planes for the block-line method)
+    alg = float(tab[:, 0].sum()) * pts * 8 * (17 if ACC.startswith("line") else 13)
     out["config5"] = dict(seconds=dt, snapshots=ns, solves_per_s=ns / dt, sweeps=[float(tab[:, 0].min()), float(tab[:, 0].max())],
                           err_max=int(tab[:, 2].max()), sweep_kernel_ms=ms, algorithmic_GBps=alg / (ms * 1e-3) / 1e9,
                           w_absmax_range=[float(tab[:, 6].min()), float(tab[:, 6].max())], efficiency_range=[float(tab[:, 5].min()), float(tab[:, 5].max())])

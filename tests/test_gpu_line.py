@@ -95,7 +95,7 @@ def test_line_chebyshev_converges_to_the_reference_solution(shape):
 def test_line_method_rejects_what_it_cannot_do():
     torch, X, O = _mods()
     with pytest.raises(RuntimeError, match="line-relaxation"):
-        X.Plan(64, 32, nbatch=2, dtype="f64", shared_coe=False, arith="fast", method="line_chebyshev")
+        X.Plan(70, 32, nbatch=2, dtype="f32", shared_coe=True, arith="fast", method="line_chebyshev")   # rows not 16-byte multiples
     with pytest.raises(RuntimeError, match="line-relaxation"):
         X.Plan(64, 32, nbatch=2, dtype="f64", shared_coe=True, arith="strict", method="line_chebyshev")
 
@@ -145,3 +145,49 @@ def test_drop_in_entry_with_the_line_method(monkeypatch):
     it, r1o, r2o, err = X.solve_elliptic(2000000, 25, 2, 5, r1, 0.0, 1.0, dat, coe, f, wk, 200, 200)
     assert err == 0 and r1o < r1 and it * 20 < ref["max_iter"], (it, ref["max_iter"])
     assert rel_l2(dat, ref["dat"]) < 1e-8
+
+
+@pytest.mark.parametrize("shape,nb", [((136, 70), 5), ((512, 256), 3)])
+def test_line_jacobi_with_one_operator_per_solve(shape, nb):
+    """Time-series layout: every solve has its own operator (and its own factors, repacked per solve)."""
+    torch, X, O = _mods()
+    nx, ny = shape
+    coes = []; Fs = []; Ps = []
+    for k in range(nb):
+        a, b, c, f, x0 = _rand_case(nx, ny, np.float64, seed=100 + k, bscale=0.02 * (k + 1))
+        coe, _ = O.cal_coe(a * (1.0 + k), b, c, 1.0, 0.5, nx, ny)
+        coes.append(coe); Fs.append(f); Ps.append(x0)
+    plan = X.Plan(nx, ny, nbatch=nb, dtype="f64", shared_coe=False, arith="fast", method="line_jacobi")
+    plan.set_coe_aos(np.stack(coes))
+    psi = torch.from_numpy(np.stack(Ps)).cuda(); ft = torch.from_numpy(np.stack(Fs)).cuda()
+    rms = plan.sweeps(psi, ft, 1.0, 5, want_rms=True)
+    plan.close()
+    got = psi.cpu().numpy()
+    for k in range(nb):
+        ref, rref = LO.line_jacobi(Ps[k], coes[k], Fs[k], 1.0, 5)
+        assert rel_l2(got[k], ref) < 1e-13, (k, rel_l2(got[k], ref))
+        assert abs(rms[k] - rref) <= 1e-11 * rref
+
+
+def test_time_series_with_the_line_method_matches_point_chebyshev():
+    """BASELINE config 5 shape on a small grid: per-snapshot operators, pumping boundary condition, thermal + dynamical
+    source; block-line Chebyshev against point Chebyshev: efficiencies within 1e-6 relative, fields within 1e-8."""
+    torch, X, O = _mods()
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.time_series import TimeSeries
+    nr, nz, ns = 256, 128, 6
+    LR, LZ = (0.0, 1.0e6), (0.0, 1.5e4)
+    params = W.series_params(ns, total=1024, first=500)
+    prm = X.SolveParams(max_iter=400000, check_step=50, converge_time=2, r1=1.0, r2=0.0, sync_every=3, stall_checks=40)
+    tabs = {}; psis = {}
+    for method in ("chebyshev", "line_chebyshev"):
+        ts = TimeSeries(nr, nz, LR, LZ, ns, "f64", arith="fast", method=method, r1_rel=1e-10)
+        tabs[method] = ts.run(params, prm)
+        psis[method] = ts.field("psi")
+        ts.close()
+    t0, t1 = tabs["chebyshev"], tabs["line_chebyshev"]
+    assert np.all(t0[:, 2] == 0) and np.all(t1[:, 2] == 0), (t0[:, 2], t1[:, 2])
+    assert np.all(np.abs(t1[:, 5] - t0[:, 5]) <= 1e-6 * np.abs(t0[:, 5]))
+    for k in range(ns):
+        assert rel_l2(psis["line_chebyshev"][k], psis["chebyshev"][k]) < 1e-8
+    assert t1[:, 0].max() * 2 <= t0[:, 0].min(), (t1[:, 0], t0[:, 0])

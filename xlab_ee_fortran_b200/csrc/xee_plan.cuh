@@ -147,7 +147,7 @@ struct Plan : PlanBase {
   const void* map_ptrs[3] = {nullptr, nullptr, nullptr};
   // v5 (segment-line relaxation, XEE_METHOD_LINE_*): Thomas factors, tiling, tensor-map cache
   bool use_line = false;
-  T* linefac = nullptr;              // [6][ny][nx]: m, u, v, w, cB, cA (line_factor_kernel)
+  T* linefac = nullptr;              // [nsets][6][ny][nx]: m, u, v, w, cB, cA (line_factor_kernel)
   unsigned char* linepack = nullptr; // operator + factors in tile/thread order
   bool linefac_ready = false;
   int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
@@ -228,14 +228,14 @@ struct Plan : PlanBase {
     use_line = d.method == XEE_METHOD_LINE_JACOBI || d.method == XEE_METHOD_LINE_CHEBYSHEV;
     if (d.method < 0 || d.method > XEE_METHOD_LINE_CHEBYSHEV) return fail("xee: unknown method");
     if (use_line) {
-      if (!d.shared_coe || d.arith != XEE_ARITH_FAST || !tma_ok)
-        return fail("xee: the line-relaxation methods need a shared operator, FAST arithmetic and nx*sizeof(real) % 16 == 0");
+      if (d.arith != XEE_ARITH_FAST || !tma_ok)
+        return fail("xee: the line-relaxation methods need FAST arithmetic and nx*sizeof(real) % 16 == 0");
       if (want != 0 && want != 5) return fail("xee: the line-relaxation methods run on sweep kernel 5 only");
       use_tma = false;
       ln_tiles_x = (d.nx + ln::TW - 1) / ln::TW; ln_tiles_y = (d.ny + ln::TH - 1) / ln::TH;
       const int nt = ln_tiles_x * ln_tiles_y;
       long long best = -1; ln_chunk = 1;
-      const int chmax = std::min(env_int("XEE_LINE_CHUNK", 32), d.nbatch), chmin = std::min(4, chmax);
+      const int chmax = d.shared_coe ? std::min(env_int("XEE_LINE_CHUNK", 32), d.nbatch) : 1, chmin = std::min(4, chmax);
       for (int ch = chmax; ch >= chmin; --ch) {
         const int nch = (d.nbatch + ch - 1) / ch;
         const long long units = (long long)nt * nch;
@@ -248,8 +248,8 @@ struct Plan : PlanBase {
         pool_free(partial); partial = nullptr;
         XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
       }
-      XEE_CHECK(pool_alloc(&linefac, sizeof(T) * kLineFacPlanes * nn));
-      XEE_CHECK(pool_alloc(&linepack, (size_t)nt * line_pack_tile_bytes<T>()));
+      XEE_CHECK(pool_alloc(&linefac, sizeof(T) * kLineFacPlanes * nn * nsets));
+      XEE_CHECK(pool_alloc(&linepack, (size_t)nt * line_pack_tile_bytes<T>() * nsets));
       want = 5;
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
@@ -392,10 +392,10 @@ struct Plan : PlanBase {
   int line_factors() {   // Thomas factors of the radial segments (v5), once per operator
     if (!use_line) return 0;
     const int nblk = (d.nx + ln::SEG * ln::BLK - 1) / (ln::SEG * ln::BLK);
-    dim3 g((nblk + 31) / 32, d.ny);
+    dim3 g((nblk + 31) / 32, d.ny, nsets);
     line_factor_kernel<T><<<g, 32, 0, own_stream>>>(coe, linefac, d.nx, d.ny);
     XEE_LAUNCH_OK();
-    line_pack_kernel<T><<<ln_tiles_x * ln_tiles_y, ln::NT, 0, own_stream>>>(coe, linefac, linepack, d.nx, d.ny, ln_tiles_x);
+    line_pack_kernel<T><<<dim3(ln_tiles_x * ln_tiles_y, nsets), ln::NT, 0, own_stream>>>(coe, linefac, linepack, d.nx, d.ny, ln_tiles_x);
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     linefac_ready = true;
@@ -497,7 +497,8 @@ struct Plan : PlanBase {
     CUtensorMap cx, cxm, cf;
     if (line_map(a.src, a.nbatch, 0, &cx) || line_map(a.f, a.nbatch, 1, &cf) || line_map(a.dst, a.nbatch, 1, &cxm)) return 1;
     LineArgs<T> A{};
-    A.pack = linepack; A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
+    A.pack = linepack; A.pack_set_stride = d.shared_coe ? 0 : (long long)(ln_tiles_x * ln_tiles_y) * (long long)line_pack_tile_bytes<T>();
+    A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
     A.alpha = a.alpha; A.omega = a.omega; A.rho_ps = a.rho_ps; A.cheb_k = a.cheb_k; A.done = a.done; A.partial = partial;
     A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;

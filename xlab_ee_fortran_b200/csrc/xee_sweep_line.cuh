@@ -7,7 +7,8 @@
 // psi' = psi - alpha z.  On the secondary-circulation operator the radial coupling carries ~97 % of the diagonal
 // (dr >> dz after the 1/(rho r) scaling), so this block-Jacobi splitting has a ~18x larger spectral gap than point
 // Jacobi and its Chebyshev acceleration needs ~4x fewer sweeps for the same residual tolerance.
-// XEE_METHOD_LINE_JACOBI / XEE_METHOD_LINE_CHEBYSHEV; FAST arithmetic, shared operator.
+// XEE_METHOD_LINE_JACOBI / XEE_METHOD_LINE_CHEBYSHEV; FAST arithmetic.  Shared operator (map: constants reloaded once
+// per chunk of solves) or one operator per solve (time series: every work unit is one (tile, solve) and reloads them).
 //
 // The block solve is split over 4 threads of a warp (partitioned / SPIKE form, everything operator-dependent
 // precomputed once per operator by line_factor_kernel):
@@ -117,7 +118,8 @@ __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_
 __device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 }  // namespace ln
 
-// Everything the block solve needs from a shared operator, once per operator: fac[6][ny][nx] =
+constexpr int kLineFacPlanes = 6;
+// Everything the block solve needs from an operator, once per operator: fac[set][6][ny][nx] =
 //   0: m(i) = 1 / (coe5(i) - lo(i) u(i-1))   1: u(i) = up(i) m(i)      Thomas factors of the 8-point segments
 //      (lo = coe4 except at a segment start, up = coe6 except at a segment end; 0 on boundary points, which therefore
 //      get a zero correction),
@@ -127,7 +129,7 @@ __device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sy
 //      true last value of the segment to the left, and a(t+1), the true first value of the segment to the right, from
 //      the end values of the four local solutions in the order a thread holds them after the two butterfly exchanges:
 //      [own first, own last, those of t^1, of t^2, of t^3].
-// One thread per (block of 32 points, row).
+// One thread per (block of 32 points, row, operator set).
 template <class T>
 __global__ void line_factor_kernel(const T* __restrict__ coe, T* __restrict__ fac, int nx, int ny) {
   constexpr int S = ln::SEG, B = ln::BLK, NB = S * B;
@@ -135,6 +137,8 @@ __global__ void line_factor_kernel(const T* __restrict__ coe, T* __restrict__ fa
   const int ib = blk * NB;
   if (ib >= nx) return;
   const size_t nn = (size_t)nx * ny;
+  coe += (size_t)blockIdx.z * kPlanes * nn;            // operator set (one per solve for a time series)
+  fac += (size_t)blockIdx.z * kLineFacPlanes * nn;
   T m[NB], u[NB], v[NB], w[NB];
   for (int t = 0; t < B; ++t) {
     T c4f = T(0), c6l = T(0);
@@ -204,7 +208,6 @@ __global__ void line_factor_kernel(const T* __restrict__ coe, T* __restrict__ fa
 // pack[tile][plane 0..10][chunk q][thread][V] (coe1..coe9, m, u), then 4 float planes [plane][chunk 0..1][thread][4]
 // (v, w, cB, cA); zeros outside the field.  A warp's 128-bit load of (plane, chunk) is one contiguous 512-byte run
 // instead of 32 rows 4 KB apart.
-constexpr int kLineFacPlanes = 6;
 template <class T> __host__ __device__ constexpr size_t line_pack_tile_bytes() {
   return (size_t)(11 * ln::Cfg<T>::NV + 4 * 2) * ln::NT * 16;
 }
@@ -216,7 +219,9 @@ __global__ void __launch_bounds__(ln::NT) line_pack_kernel(const T* __restrict__
   const int sg = ln::seg_of(tid), r = ln::row_of(tid);
   const int gi = (tile % tiles_x) * ln::TW + ln::SEG * sg, gj = (tile / tiles_x) * ln::TH + r;
   const size_t nn = (size_t)nx * ny;
-  unsigned char* base = pack + (size_t)tile * line_pack_tile_bytes<T>();
+  coe += (size_t)blockIdx.y * kPlanes * nn;
+  fac += (size_t)blockIdx.y * kLineFacPlanes * nn;
+  unsigned char* base = pack + ((size_t)blockIdx.y * gridDim.x + tile) * line_pack_tile_bytes<T>();
   T* out = reinterpret_cast<T*>(base);
   float* aux = reinterpret_cast<float*>(base + (size_t)11 * C::NV * ln::NT * 16);
   for (int k = 0; k < 15; ++k) {
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(ln::NT) line_pack_kernel(const T* __restrict__
 template <class T>
 struct LineArgs {
   const unsigned char* pack;   // operator + factors in tile/thread order (line_pack_kernel)
+  long long pack_set_stride;   // bytes between the packs of consecutive solves; 0 = one shared operator
   T* dst;                  // psi_{k+1} (holds psi_{k-1} on entry: read through map_xm at the own cells only)
   long long field_stride;  // nx*ny
   int nx, ny, nbatch;
@@ -326,7 +332,8 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
     T cf[9][SEG];
     float cB[SEG], cA[SEG];
     {
-      const unsigned char* pb = a.pack + (size_t)tile * line_pack_tile_bytes<T>();
+      // one operator per solve: the host makes every unit one solve (chunk = 1), so n0 names the operator set
+      const unsigned char* pb = a.pack + (size_t)n0 * a.pack_set_stride + (size_t)tile * line_pack_tile_bytes<T>();
       const T* pk = reinterpret_cast<const T*>(pb) + (size_t)tid * V;
       const float* pa = reinterpret_cast<const float*>(pb + (size_t)11 * NV * NT * 16) + (size_t)tid * 4;
 #pragma unroll

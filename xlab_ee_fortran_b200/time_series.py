@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from .efficiency_map import _prm
-from .plan import ARITH_FAST, ARITH_STRICT, CHEBYSHEV, F32, F64, JACOBI, SolveParams
+from .plan import ARITH_FAST, ARITH_STRICT, CHEBYSHEV, F32, F64, JACOBI, METHODS, SolveParams
 
 COLS = ("iters", "r1", "err", "sum_Q", "ke_gen", "efficiency", "w_absmax", "u_absmax")
 
@@ -25,7 +25,7 @@ class TimeSeries:
         self.nr, self.nz, self.nsnap = int(nr), int(nz), int(nsnap)
         self.np_dtype = np.float64 if dtype == "f64" else np.float32
         d = _SeriesDesc(F64 if dtype == "f64" else F32, nr, nz, nsnap, density_mode,
-                        ARITH_STRICT if arith == "strict" else ARITH_FAST, CHEBYSHEV if method == "chebyshev" else JACOBI,
+                        ARITH_STRICT if arith == "strict" else ARITH_FAST, METHODS[method],
                         device, (C.c_double * 2)(*Lr), (C.c_double * 2)(*Lz), float(r1_rel))
         self._h = C.c_void_p()
         _lib.check(_lib.lib().xee_series_create(C.byref(d), C.byref(self._h)), "series_create")
