@@ -191,3 +191,21 @@ def test_time_series_with_the_line_method_matches_point_chebyshev():
     for k in range(ns):
         assert rel_l2(psis["line_chebyshev"][k], psis["chebyshev"][k]) < 1e-8
     assert t1[:, 0].max() * 2 <= t0[:, 0].min(), (t1[:, 0], t0[:, 0])
+
+
+def test_rehosted_driver_on_test1_with_the_line_method(tmp_path, monkeypatch):
+    """BASELINE config 1 end to end (the reference's diag.txt, real(4) .bin files in and out) with
+    XEE_METHOD=line_chebyshev XEE_ARITH=fast: same stop rule (r1 = r2 = 5e-3), same converged field and eta as the
+    reference iteration within the real(4) round-off floor the reference itself stops on."""
+    from tests.test_gpu_parity import _run_diagnose
+    from tests.util import golden_json
+    gj = golden_json()
+    monkeypatch.setenv("XEE_METHOD", "line_chebyshev"); monkeypatch.setenv("XEE_ARITH", "fast")
+    monkeypatch.setenv("XEE_STALL_CHECKS", "10")   # the ratio criterion is noise on the real(4) floor of an accelerated method
+    out = _run_diagnose(tmp_path, gj["reference_test1_diag_txt"])
+    assert " Elliptic Tools: Iteration success." in out
+    rchi = np.fromfile(tmp_path / "rchi-[BAROTROPIC]-O.bin", np.float32).reshape(200, 200)
+    gold = gj["test1"]["f32"]
+    assert np.sqrt((rchi.astype(np.float64) ** 2).sum()) == pytest.approx(gold["psi_stop_l2"], rel=2e-4)
+    eta = np.fromfile(tmp_path / "eta-[BAROTROPIC]-A.bin", np.float32)
+    assert float(eta.max()) == pytest.approx(gold["eta_stop_max"], rel=2e-3)
