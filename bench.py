@@ -166,7 +166,15 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly ONE JSON line: NCCL prints "NCCL version ..." there when NCCL_DEBUG is WARN/VERSION, so the
+        # communicator is created (first collective) with stdout pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1); os.close(saved)
     total = args.nheat * world
     rows = heat_rows(total)
     a, b = partition(total, world, rank)
