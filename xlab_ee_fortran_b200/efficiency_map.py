@@ -31,7 +31,7 @@ def _prm(p: SolveParams):
 class EfficiencyMap:
     """Holds the vortex operator on one GPU and solves `nheat` heating locations per run()."""
 
-    def __init__(self, A, B, Cf, Lr, Lz, nheat, dtype="f64", density_mode=0, arith="fast", method="chebyshev",
+    def __init__(self, A, B, Cf, Lr, Lz, nheat, dtype="f64", density_mode=0, arith="fast", method="line_chebyshev",
                  adjoint_check=False, r1_rel=1e-12, device=-1):
         _lib.require_gpu()
         A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32); Cf = np.ascontiguousarray(Cf, np.float32)

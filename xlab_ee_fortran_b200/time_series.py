@@ -19,7 +19,7 @@ class _SeriesDesc(C.Structure):
 
 
 class TimeSeries:
-    def __init__(self, nr, nz, Lr, Lz, nsnap, dtype="f64", density_mode=0, arith="fast", method="chebyshev", r1_rel=1e-12,
+    def __init__(self, nr, nz, Lr, Lz, nsnap, dtype="f64", density_mode=0, arith="fast", method="line_chebyshev", r1_rel=1e-12,
                  device=-1):
         _lib.require_gpu()
         self.nr, self.nz, self.nsnap = int(nr), int(nz), int(nsnap)
