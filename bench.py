@@ -10,6 +10,11 @@ built on the device, all solves to tolerance, energy integrals, efficiency table
   python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host cores
 
+Method (`--method`, default line_chebyshev): Chebyshev-accelerated block-line relaxation (v5 kernel; same residual, tolerance
+and stop rule as solve_elliptic, 32-point radial blocks solved inside the sweep); `chebyshev` = accelerated point Jacobi on
+the temporally blocked kernel (v4); `jacobi` = the reference iteration.  Results of all three agree within the north_star
+tolerances (tests/test_gpu_map.py, tests/test_gpu_line.py).
+
 `value`  : whole-job solves/s with the operator and heating parameters resident in HBM.
 `e2e`    : the same metric through the host-facing call (HOST A,B,C + heating table in, efficiency
            table out; H2D/D2H and operator assembly inside the timed region).
