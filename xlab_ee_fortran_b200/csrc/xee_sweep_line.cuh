@@ -27,10 +27,15 @@
 //   * warp = 32 columns x 8 rows (lane = segment-in-block * 8 + row).  TMA boxes are 70 (psi, with halo) and 66
 //     (f, psi_{k-1}) elements wide, i.e. an ODD number of 16-byte chunks per shared-memory row, so the 128-bit loads of
 //     8 lanes with the same columns and consecutive rows hit distinct banks without any swizzle;
-//   * one persistent CTA of 256 threads per SM, tiles of 64 x 32 points, 3-stage TMA ring, one named barrier per
-//     (tile, solve) to hand the stage back; results go to global memory as 128-bit stores;
+//   * TWO persistent CTAs of 128 threads per SM (255 registers per thread: the register file is full), tiles of
+//     64 x 16 points, a 2-stage TMA ring per CTA (80 KB of shared memory each), one named barrier per (tile, solve) to
+//     hand the stage back; while one CTA reloads the operator of its next work unit or waits at its barrier the other
+//     one computes.  Results go to global memory as 128-bit stores;
 //   * the operator and the factors are repacked once per operator in tile/thread order (line_pack_kernel), so the
 //     per-unit reload of a thread's constants is fully coalesced 128-bit loads (2-3 us per unit instead of 10).
+// Measured on B200 (512 solves, 512x256, fp64, Chebyshev): 377 us per sweep = 5.66 TB/s algorithmic (87 % of the measured
+// copy peak) with a shared operator; 6.1 TB/s of 136 B/point with one operator per solve (one CTA per SM on 64 x 32 tiles
+// with a 3-stage ring, XEE_LINE_TH=32 XEE_LINE_NSTAGE=3: 391 us and 4.4 TB/s).
 #pragma once
 #include <cuda.h>
 
@@ -44,14 +49,14 @@ namespace ln {
 constexpr int SEG = 8;             // points per thread
 constexpr int BLK = 4;             // threads per block of the line relaxation: blocks of SEG * BLK = 32 radial points
 #ifndef XEE_LINE_TH
-#define XEE_LINE_TH 32
+#define XEE_LINE_TH 16
 #endif
 constexpr int TW = 64, TH = XEE_LINE_TH;    // tile (grid points); TH = 16 runs two CTAs of 128 threads per SM
 constexpr int CTAS_PER_SM = 32 / TH;
 constexpr int NSEG = TW / SEG;     // 8 warps
 constexpr int NT = NSEG * TH;      // 256 threads
 #ifndef XEE_LINE_NSTAGE
-#define XEE_LINE_NSTAGE 3
+#define XEE_LINE_NSTAGE 2
 #endif
 constexpr int NSTAGE = XEE_LINE_NSTAGE;
 template <class T> struct Cfg {
