@@ -76,7 +76,9 @@ template <class T>
 struct DevBuf {
   T* p = nullptr; size_t n = 0;
   explicit DevBuf(size_t n_) : n(n_) { if (pool_alloc(&p, sizeof(T) * (n ? n : 1)) != cudaSuccess) { g_last_error = "cudaMalloc"; die("DevBuf"); } }
-  DevBuf(const T* host, size_t n_) : DevBuf(n_) { if (cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "H2D"; die("DevBuf"); } }
+  // a pageable H2D cudaMemcpy may return before the DMA has landed, and the plans work on non-blocking streams that the
+  // legacy default stream does not order: synchronise the device before anyone reads the buffer
+  DevBuf(const T* host, size_t n_) : DevBuf(n_) { if (cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { g_last_error = "H2D"; die("DevBuf"); } }
   ~DevBuf() { pool_free(p); }
   void to_host(T* host) const { if (cudaMemcpy(host, p, sizeof(T) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { g_last_error = "D2H"; die("DevBuf"); } }
 };

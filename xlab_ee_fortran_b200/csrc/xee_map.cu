@@ -164,7 +164,7 @@ struct Map : MapBase {
       r[6] = hi[3 * n + 2]; r[7] = r[6] / r[3];
     }
     if (table_on_host) memcpy(table, rows.data(), sizeof(double) * rows.size());
-    else XEE_CHECK(cudaMemcpy(table, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice));
+    else { XEE_CHECK(cudaMemcpyAsync(table, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice, s)); XEE_CHECK(cudaStreamSynchronize(s)); }
     return 0;
   }
   int get_field(int which, void* out) override {

@@ -167,7 +167,9 @@ struct Plan : PlanBase {
     nsets = d.shared_coe ? 1 : d.nbatch;
     XEE_CHECK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     XEE_CHECK(pool_alloc(&coe, sizeof(T) * kPlanes * nn * nsets));
-    XEE_CHECK(cudaMemset(coe, 0, sizeof(T) * kPlanes * nn * nsets));
+    // on the plan's own (non-blocking) stream: a cudaMemset on the legacy default stream is asynchronous and NOT ordered with
+    // it, and could land after the operator assembly (seen under multi-process timing: a zeroed operator, NaN factors)
+    XEE_CHECK(cudaMemsetAsync(coe, 0, sizeof(T) * kPlanes * nn * nsets, own_stream));
     XEE_CHECK(pool_alloc(&x1, sizeof(T) * nn * d.nbatch));
     const int nb = d.nbatch;
     XEE_CHECK(pool_alloc(&st.done, sizeof(int) * nb)); XEE_CHECK(pool_alloc(&st.iters, sizeof(int) * nb));
@@ -778,7 +780,12 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   }
   for (int n = 0; n < ns && !rc; ++n) {
     rho[n] = nA[n] > 0 ? nB[n] / nA[n] : 0.0;
-    if (!(rho[n] > 0.0 && rho[n] < 1.0)) rc = fail("xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant?");
+    if (!(rho[n] > 0.0 && rho[n] < 1.0)) {
+      char msg[320];
+      snprintf(msg, sizeof msg, "xee: Jacobi spectral-radius estimate outside (0,1); operator not diagonally dominant? "
+               "[set %d of %d: |G^%d e| = %.6e, |G^%d e| = %.6e, ratio %.9f, line=%d]", n, ns, itA - 1, nA[n], itA, nB[n], rho[n], (int)use_line);
+      rc = fail(msg);
+    }
   }
   // ---- stage B
   const int rounds = env_int("XEE_RHO_ROUNDS", 4), p = env_int("XEE_RHO_PROBE", use_line ? 64 : 200);
