@@ -119,3 +119,26 @@ def test_full_size_map_shard_properties(method):
     # common tolerance at 512x256.  Same-iteration parity (STRICT Jacobi vs the oracle) is bit-exact elsewhere.
     assert rel_l2(pj[0], psi[3]) < 5e-8 and rel_l2(pj[1], psi[77]) < 5e-8
     assert np.allclose(tj[:, 5], tab[[3, 77], 5], rtol=1e-6)              # efficiency within 1e-6 relative
+
+
+def test_plans_do_not_depend_on_the_legacy_default_stream():
+    """Regression: Plan::init once cleared the operator with cudaMemset on the legacy default stream, which a plan's
+    non-blocking stream does not order.  With the default stream busy (here: queued torch work; in the multi-GPU bench it was
+    timing) the clear landed AFTER the operator assembly and the solve ran on a zeroed operator.  A map created while the
+    default stream is busy must give the same table as one created on an idle device."""
+    import torch
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200.efficiency_map import EfficiencyMap
+    nr, nz = 64, 32
+    A, B, C, Lr, Lz, heat = _setup(nr, nz)
+    prm = X.SolveParams(max_iter=50000, check_step=25, converge_time=2, r1=1.0, r2=0.0)
+    torch.cuda.synchronize()
+    m = EfficiencyMap(A, B, C, Lr, Lz, len(heat), "f64", r1_rel=1e-10)
+    ref = m.run(heat, prm); m.close()
+    a = torch.randn(4096, 4096, device="cuda")
+    for _ in range(60):                       # ~100 ms of work queued on the default stream
+        a = torch.tanh(a @ a * 1e-2)
+    m = EfficiencyMap(A, B, C, Lr, Lz, len(heat), "f64", r1_rel=1e-10)
+    tab = m.run(heat, prm); m.close()
+    torch.cuda.synchronize()
+    assert np.array_equal(tab, ref)
