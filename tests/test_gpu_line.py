@@ -22,7 +22,7 @@ def _batch(nx, ny, nb, dt, seed):
 
 
 @pytest.mark.parametrize("shape,nb", [((512, 256), 3), ((200, 200), 2), ((140, 70), 5), ((72, 40), 40), ((64, 32), 7),
-                                      ((8, 4), 3), ((260, 13), 9)])
+                                      ((8, 4), 3), ((260, 13), 9), ((128, 40), 5), ((192, 23), 33)])   # last two: TMA-store path, ragged rows
 @pytest.mark.parametrize("sweeps", [1, 2, 7])
 def test_line_jacobi_sweeps_match_numpy_restatement(shape, nb, sweeps):
     torch, X, O = _mods()

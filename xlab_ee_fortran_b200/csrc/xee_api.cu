@@ -25,24 +25,31 @@ int xee_plan_create(const xee_plan_desc* desc, xee_plan** out) {
   *out = new xee_plan{p};
   return 0;
 }
-int xee_plan_destroy(xee_plan* p) { if (p) { delete p->impl; delete p; } return 0; }
-int xee_plan_set_coe_aos_host(xee_plan* p, const void* c) { return p->impl->set_coe_aos(c, true); }
-int xee_plan_set_coe_aos_dev(xee_plan* p, const void* c) { return p->impl->set_coe_aos(c, false); }
+// Every plan entry point runs with the plan's device current (and restores the caller's): a process may hold plans on
+// several GPUs.
+int xee_plan_destroy(xee_plan* p) { if (p) { DeviceGuard g(p->impl->d.device); delete p->impl; delete p; } return 0; }
+int xee_plan_set_coe_aos_host(xee_plan* p, const void* c) { DeviceGuard g(p->impl->d.device); return p->impl->set_coe_aos(c, true); }
+int xee_plan_set_coe_aos_dev(xee_plan* p, const void* c) { DeviceGuard g(p->impl->d.device); return p->impl->set_coe_aos(c, false); }
 int xee_plan_set_abc_dev(xee_plan* p, const void* a, const void* b, const void* c, double dx, double dy) {
+  DeviceGuard g(p->impl->d.device);
   return p->impl->set_abc(a, b, c, dx, dy);
 }
 int xee_plan_solve_dev(xee_plan* p, void* psi, const void* f, const xee_solve_params* prm, int* iters, double* r1o,
                        double* r2o, int* err, void* stream) {
+  DeviceGuard g(p->impl->d.device);
   return p->impl->solve(psi, f, prm, iters, r1o, r2o, err, (cudaStream_t)stream, false, nullptr, 0);
 }
 int xee_plan_solve_host(xee_plan* p, void* psi, const void* f, const xee_solve_params* prm, int* iters, double* r1o,
                         double* r2o, int* err) {
+  DeviceGuard g(p->impl->d.device);
   return p->impl->solve(psi, f, prm, iters, r1o, r2o, err, nullptr, true, nullptr, 0);
 }
 int xee_plan_sweeps_dev(xee_plan* p, void* psi, const void* f, double alpha, int sweeps, double* rms, void* stream) {
+  DeviceGuard g(p->impl->d.device);
   return p->impl->sweeps(psi, f, alpha, sweeps, rms, (cudaStream_t)stream);
 }
 int xee_plan_apply_dev(xee_plan* p, const void* psi, void* out, void* stream) {
+  DeviceGuard g(p->impl->d.device);
   return p->impl->apply(psi, out, (cudaStream_t)stream);
 }
 int xee_sweep_kernel_stats(xee_plan* p, double* ms, long long* launches, int reset) {
@@ -184,18 +191,25 @@ void solve_elliptic_old_impl(const int* max_iter, int* strategy, T* strategy_r, 
                              const T* f, T* workspace, const int* nx, const int* ny, int* err, const int* debug) {
   *err = 0;
   if (*strategy != 1 && *strategy != 2) { *err = 1 << 8; fprintf(stderr, "xee_b200: legacy strategy %d (max-abs residual) is not provided\n", *strategy); return; }
-  // the legacy loop tests cnt == max_iter only on check sweeps, so the effective bound is the last multiple of 100
-  const int eff_max = (*max_iter / 100) * 100;
-  if (eff_max <= 0) { memcpy(workspace, dat, sizeof(T) * (size_t)*nx * *ny); return; }
+  // The legacy loop `do cnt = 1, max_iter` (:168) runs ALL max_iter sweeps; the stop tests and `cnt == max_iter` are evaluated
+  // on check sweeps only (every 100th, :293-305).  A run that never stops on a check and whose max_iter is not a multiple of
+  // 100 therefore falls out of the loop with err = 0, strategy / strategy_r untouched and judge_error not called.
+  const int mi = *max_iter;
+  if (mi <= 0) { memcpy(workspace, dat, sizeof(T) * (size_t)*nx * *ny); return; }
   PlanBase* p = new_plan_or_die(dtype_of<T>(), *nx, *ny, 1, 1);
   if (p->set_coe_aos(coe, true)) die("solve_elliptic(old)");
   xee_solve_params prm{};
-  prm.max_iter = eff_max; prm.check_step = 100; prm.alpha = (double)*alpha; prm.sync_every = 2;
+  prm.max_iter = mi; prm.check_step = 100; prm.alpha = (double)*alpha; prm.sync_every = 2;
+  prm.detect_explode = 1;   // the legacy isnan tests (:218-240) set err_explode; here: a non-finite residual at a check
   if (*strategy == 1) { prm.r1 = (double)*strategy_r; prm.r2 = 0.0; prm.converge_time = 1; prm.lost_rate = 5; if (!(prm.r1 > 0)) prm.r1 = 1e-300; }
   else { prm.r1 = 0.0; prm.r2 = (double)*strategy_r; prm.converge_time = 10; prm.lost_rate = 5; if (!(prm.r2 > 0)) prm.r2 = 1e-300; }
   int iters = 0, e = 0; double r1o = 0, r2o = 0;
   if (p->solve(dat, f, &prm, &iters, &r1o, &r2o, &e, nullptr, true, workspace, *debug == 1 ? 2 : 0)) die("solve_elliptic(old)");
   delete p;
+  if ((mi % 100) != 0 && iters == mi && (e & XEE_ERR_OVER_MAX_ITERATION)) {   // fell out of the loop between two checks
+    *err = e & ~XEE_ERR_OVER_MAX_ITERATION;
+    return;
+  }
   *err = e; *strategy = iters; *strategy_r = (T)r1o;
   xee_judge_error(err);
 }

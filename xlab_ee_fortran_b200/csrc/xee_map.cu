@@ -18,6 +18,7 @@ namespace xee {
 
 struct MapBase {
   xee_map_desc d{};
+  int device() const { return d.device; }
   virtual ~MapBase() {}
   virtual int run(const double* heat, bool heat_on_host, const xee_solve_params* prm, double* table, bool table_on_host,
                   cudaStream_t s) = 0;
@@ -193,24 +194,29 @@ extern "C" {
 int xee_map_create(const xee_map_desc* desc, const float* A, const float* B, const float* C, xee_map** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("xee: no CUDA device available - this library has no CPU fallback");
-  if (desc->device >= 0) XEE_CHECK(cudaSetDevice(desc->device));
+  int dev = desc->device;
+  if (dev < 0) XEE_CHECK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail("xee: device index out of range");
+  DeviceGuard guard(dev);
   if (desc->nr < 4 || desc->nz < 4 || desc->nheat < 1) return fail("xee_map: nr, nz >= 4 and nheat >= 1 required");
   MapBase* m = nullptr; int rc;
-  if (desc->dtype == XEE_F32) { auto* q = new Map<float>(); q->d = *desc; rc = q->init(A, B, C); m = q; }
-  else if (desc->dtype == XEE_F64) { auto* q = new Map<double>(); q->d = *desc; rc = q->init(A, B, C); m = q; }
+  if (desc->dtype == XEE_F32) { auto* q = new Map<float>(); q->d = *desc; q->d.device = dev; rc = q->init(A, B, C); m = q; }
+  else if (desc->dtype == XEE_F64) { auto* q = new Map<double>(); q->d = *desc; q->d.device = dev; rc = q->init(A, B, C); m = q; }
   else return fail("xee_map: dtype must be XEE_F32 or XEE_F64");
   if (rc) { delete m; return 1; }
   *out = new xee_map{m};
   return 0;
 }
-int xee_map_destroy(xee_map* m) { if (m) { delete m->impl; delete m; } return 0; }
+int xee_map_destroy(xee_map* m) { if (m) { DeviceGuard g(m->impl->device()); delete m->impl; delete m; } return 0; }
 int xee_map_run_host(xee_map* m, const double* heat, const xee_solve_params* prm, double* table) {
+  DeviceGuard g(m->impl->device());
   return m->impl->run(heat, true, prm, table, true, nullptr);
 }
 int xee_map_run_dev(xee_map* m, const double* heat_dev, const xee_solve_params* prm, double* table_dev, void* stream) {
+  DeviceGuard g(m->impl->device());
   return m->impl->run(heat_dev, false, prm, table_dev, false, (cudaStream_t)stream);
 }
-int xee_map_get_field(xee_map* m, int which, void* host_out) { return m->impl->get_field(which, host_out); }
+int xee_map_get_field(xee_map* m, int which, void* host_out) { DeviceGuard g(m->impl->device()); return m->impl->get_field(which, host_out); }
 int xee_map_sweep_kernel_stats(xee_map* m, double* ms, long long* launches, int reset) {
   PlanBase* p = m->impl->plan();
   if (ms) *ms = p->sweep_ms;

@@ -42,6 +42,33 @@ extern std::atomic<long long> g_launches;
 
 inline int fail(const char* msg) { g_last_error = msg; return 1; }
 
+// The dynamic-shared-memory opt-in is a per-DEVICE function attribute: set it once per (kernel instantiation, device).
+template <class K>
+inline int opt_in_smem(K kernel, int bytes, std::atomic<unsigned long long>& done_mask) {
+  int dev = 0;
+  XEE_CHECK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit) return 0;
+  if (bytes < 0) {   // everything the SM has left beside the kernel's static shared memory
+    cudaFuncAttributes fa{};
+    XEE_CHECK(cudaFuncGetAttributes(&fa, kernel));
+    bytes = 227 * 1024 - (int)fa.sharedSizeBytes;
+  }
+  XEE_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done_mask.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+
+// Makes the plan's device current for the duration of an entry point and restores the caller's device afterwards.
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -152,7 +179,8 @@ struct Plan : PlanBase {
   bool linefac_ready = false;
   int ln_tiles_x = 0, ln_tiles_y = 0, ln_chunk = 1, ln_nchunks = 1;
   struct LineMap { const void* ptr; int nb; int kind; CUtensorMap map; };
-  std::vector<LineMap> line_maps;    // kind 0: psi box (with halo), 1: f / psi_{k-1} box
+  std::vector<LineMap> line_maps;    // kind 0: psi box (with halo), 1: f / psi_{k-1} box, 2: 4-D store view of the result
+  bool ln_tstore = false;            // results leave through TMA stores (nx a multiple of the tile width)
   bool method_is_cheb() const { return d.method == XEE_METHOD_CHEBYSHEV || d.method == XEE_METHOD_LINE_CHEBYSHEV; }
   // v4 (temporal blocking) sweep kernel: two more iterate buffers (passes cannot update in place), tiling, maps
   bool use_tb = false;
@@ -246,6 +274,7 @@ struct Plan : PlanBase {
         if (best < 0 || makespan < best) { best = makespan; ln_chunk = ch; }
       }
       ln_nchunks = (d.nbatch + ln_chunk - 1) / ln_chunk;
+      ln_tstore = d.nx % ln::TW == 0 && env_int("XEE_LINE_TSTORE", 1) != 0;
       if (nt > ntiles) {
         pool_free(partial); partial = nullptr;
         XEE_CHECK(pool_alloc(&partial, sizeof(double) * (size_t)nt * nb));
@@ -347,6 +376,25 @@ struct Plan : PlanBase {
     if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "xee: cuTensorMapEncodeTiled(4D) failed (%d)", (int)r); return fail(b); }
     return 0;
   }
+  // 4-D view of a field batch for the TMA stores of the v5 kernel: (column within a TW-wide tile column, tile column, row,
+  // solve).  A [TH][FW] staging box stored at column 0 loses its FW - TW pad columns as out-of-bounds elements.
+  int encode_map_out(CUtensorMap* m, const void* base, int nb) {
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    XEE_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p) return fail("xee: cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)ln::TW, (cuuint64_t)(d.nx / ln::TW), (cuuint64_t)d.ny, (cuuint64_t)nb};
+    const cuuint64_t strides[3] = {(cuuint64_t)ln::TW * sizeof(T), (cuuint64_t)d.nx * sizeof(T), (cuuint64_t)d.nx * d.ny * sizeof(T)};
+    const cuuint32_t box[4] = {(cuuint32_t)ln::Cfg<T>::FW, 1, (cuuint32_t)ln::TH, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = ((Fn)p)(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                               const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "xee: cuTensorMapEncodeTiled(store view) failed (%d)", (int)r); return fail(b); }
+    return 0;
+  }
   ~Plan() override {
     { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
@@ -443,14 +491,8 @@ struct Plan : PlanBase {
     constexpr int coe_off = tma::Cfg<T>::PSI_BYTES + tma::Cfg<T>::FLD_BYTES + (MODE == MODE_CHEBYSHEV ? tma::Cfg<T>::FLD_BYTES : 0);
     constexpr int stage = coe_off + (PERSOLVE ? (kPlanes * tma::Cfg<T>::FLD_RAW + 127) / 128 * 128 : 0);
     const size_t smem = (size_t)stage * P.nstage;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncAttributes fa{};
-      XEE_CHECK(cudaFuncGetAttributes(&fa, sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>));
-      XEE_CHECK(cudaFuncSetAttribute(sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024 - (int)fa.sharedSizeBytes));
-      attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (opt_in_smem(sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE>, -1, attr_done)) return 1;
     sweep_tma_kernel<T, ARITH, MODE, CHECK, PERSOLVE><<<tma_grid, tma::NTHREADS, smem, s>>>(P, ms, mp, map_f, map_coe);
     return 0;
   }
@@ -477,37 +519,37 @@ struct Plan : PlanBase {
   int line_map(const void* ptr, int nb, int kind, CUtensorMap* out) {
     for (auto& m : line_maps) if (m.ptr == ptr && m.nb == nb && m.kind == kind) { *out = m.map; return 0; }
     if ((uintptr_t)ptr & 15) return fail("xee: TMA path needs 16-byte aligned field buffers");
-    if (line_maps.size() >= 16) line_maps.erase(line_maps.begin());
+    if (line_maps.size() >= 24) line_maps.erase(line_maps.begin());
     LineMap lm{ptr, nb, kind, {}};
-    if (kind == 0 ? encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::XW, ln::TH + 2) : encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::FW, ln::TH)) return 1;
+    if (kind == 0 ? encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::XW, ln::TH + 2)
+        : kind == 1 ? encode_map(&lm.map, ptr, d.nx, d.ny, nb, ln::Cfg<T>::FW, ln::TH) : encode_map_out(&lm.map, ptr, nb)) return 1;
     line_maps.push_back(lm);
     *out = lm.map;
     return 0;
   }
   template <bool CHEB, bool CHECK>
-  int launch_line_inst(const LineArgs<T>& A, int grid, const CUtensorMap& mx, const CUtensorMap& mxm, const CUtensorMap& mf, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      XEE_CHECK(cudaFuncSetAttribute(sweep_line_kernel<T, CHEB, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln::Cfg<T>::SMEM_BYTES));
-      attr_done = true;
-    }
-    sweep_line_kernel<T, CHEB, CHECK><<<grid, ln::NT, ln::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, mf);
+  int launch_line_inst(const LineArgs<T>& A, int grid, const CUtensorMap& mx, const CUtensorMap& mxm, const CUtensorMap& mf, const CUtensorMap& mo, cudaStream_t s) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (opt_in_smem(sweep_line_kernel<T, CHEB, CHECK>, ln::Cfg<T>::SMEM_BYTES, attr_done)) return 1;
+    sweep_line_kernel<T, CHEB, CHECK><<<grid, ln::NT, ln::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, mf, mo);
     return 0;
   }
   int launch_sweep_line(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
     if (!linefac_ready) return fail("xee: line relaxation: the operator has not been set");
-    CUtensorMap cx, cxm, cf;
+    CUtensorMap cx, cxm, cf, co;
     if (line_map(a.src, a.nbatch, 0, &cx) || line_map(a.f, a.nbatch, 1, &cf) || line_map(a.dst, a.nbatch, 1, &cxm)) return 1;
+    if (ln_tstore) { if (line_map(a.dst, a.nbatch, 2, &co)) return 1; } else co = cxm;
     LineArgs<T> A{};
     A.pack = linepack; A.pack_set_stride = d.shared_coe ? 0 : (long long)(ln_tiles_x * ln_tiles_y) * (long long)line_pack_tile_bytes<T>();
     A.dst = a.dst; A.field_stride = (long long)nn; A.nx = d.nx; A.ny = d.ny; A.nbatch = a.nbatch;
     A.alpha = a.alpha; A.omega = a.omega; A.rho_ps = a.rho_ps; A.cheb_k = a.cheb_k; A.done = a.done; A.partial = partial;
     A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
+    A.tstore = ln_tstore ? 1 : 0;
     const int grid = (int)std::min<long long>((long long)num_sms * ln::CTAS_PER_SM, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
     int rc;
-    if (mode == MODE_CHEBYSHEV) rc = check ? launch_line_inst<true, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<true, false>(A, grid, cx, cxm, cf, s);
-    else rc = check ? launch_line_inst<false, true>(A, grid, cx, cxm, cf, s) : launch_line_inst<false, false>(A, grid, cx, cxm, cf, s);
+    if (mode == MODE_CHEBYSHEV) rc = check ? launch_line_inst<true, true>(A, grid, cx, cxm, cf, co, s) : launch_line_inst<true, false>(A, grid, cx, cxm, cf, co, s);
+    else rc = check ? launch_line_inst<false, true>(A, grid, cx, cxm, cf, co, s) : launch_line_inst<false, false>(A, grid, cx, cxm, cf, co, s);
     if (rc) return rc;
     XEE_LAUNCH_OK();
     return 0;
@@ -538,11 +580,8 @@ struct Plan : PlanBase {
   }
   template <int ARITH, int MODE, bool CHECK>
   int launch_tb_inst(const TbArgs<T>& A, const CUtensorMap& mx, const CUtensorMap& mxm, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      XEE_CHECK(cudaFuncSetAttribute(sweep_tb_kernel<T, ARITH, MODE, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb::Cfg<T>::SMEM_BYTES));
-      attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (opt_in_smem(sweep_tb_kernel<T, ARITH, MODE, CHECK>, tb::Cfg<T>::SMEM_BYTES, attr_done)) return 1;
     sweep_tb_kernel<T, ARITH, MODE, CHECK><<<tb_grid, tb::NT, tb::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, map_tb_f);
     return 0;
   }
@@ -1048,11 +1087,14 @@ inline int make_plan(const xee_plan_desc* desc, PlanBase** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("xee: no CUDA device available - this library has no CPU fallback");
   if (desc->nx < 3 || desc->ny < 3 || desc->nbatch < 1) return fail("xee: nx, ny >= 3 and nbatch >= 1 required");
-  if (desc->device >= 0) XEE_CHECK(cudaSetDevice(desc->device));
+  int dev = desc->device;
+  if (dev < 0) XEE_CHECK(cudaGetDevice(&dev));      // "current device", resolved so that later entry points can return to it
+  if (dev >= ndev) return fail("xee: device index out of range");
+  DeviceGuard guard(dev);
   PlanBase* p = nullptr;
   int rc;
-  if (desc->dtype == XEE_F32) { auto* q = new Plan<float>(); q->d = *desc; rc = q->init(); p = q; }
-  else if (desc->dtype == XEE_F64) { auto* q = new Plan<double>(); q->d = *desc; rc = q->init(); p = q; }
+  if (desc->dtype == XEE_F32) { auto* q = new Plan<float>(); q->d = *desc; q->d.device = dev; rc = q->init(); p = q; }
+  else if (desc->dtype == XEE_F64) { auto* q = new Plan<double>(); q->d = *desc; q->d.device = dev; rc = q->init(); p = q; }
   else return fail("xee: dtype must be XEE_F32 or XEE_F64");
   if (rc) { delete p; return 1; }
   *out = p;

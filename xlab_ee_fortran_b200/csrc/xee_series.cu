@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const T* __restrict__ x, lo
 
 struct SeriesBase {
   xee_series_desc d{};
+  int device() const { return d.device; }
   virtual ~SeriesBase() {}
   virtual int run(const double* params_host, const xee_solve_params* prm, double* table_host) = 0;
   virtual int get_field(int which, void* host_out) = 0;
@@ -271,19 +272,22 @@ extern "C" {
 int xee_series_create(const xee_series_desc* desc, xee_series** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("xee: no CUDA device available - this library has no CPU fallback");
-  if (desc->device >= 0) XEE_CHECK(cudaSetDevice(desc->device));
+  int dev = desc->device;
+  if (dev < 0) XEE_CHECK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail("xee: device index out of range");
+  DeviceGuard guard(dev);
   if (desc->nr < 4 || desc->nz < 5 || desc->nsnap < 1) return fail("xee_series: nr >= 4, nz >= 5 and nsnap >= 1 required");
   SeriesBase* m = nullptr; int rc;
-  if (desc->dtype == XEE_F32) { auto* q = new Series<float>(); q->d = *desc; rc = q->init(); m = q; }
-  else if (desc->dtype == XEE_F64) { auto* q = new Series<double>(); q->d = *desc; rc = q->init(); m = q; }
+  if (desc->dtype == XEE_F32) { auto* q = new Series<float>(); q->d = *desc; q->d.device = dev; rc = q->init(); m = q; }
+  else if (desc->dtype == XEE_F64) { auto* q = new Series<double>(); q->d = *desc; q->d.device = dev; rc = q->init(); m = q; }
   else return fail("xee_series: dtype must be XEE_F32 or XEE_F64");
   if (rc) { delete m; return 1; }
   *out = new xee_series{m};
   return 0;
 }
-int xee_series_destroy(xee_series* m) { if (m) { delete m->impl; delete m; } return 0; }
-int xee_series_run_host(xee_series* m, const double* params, const xee_solve_params* prm, double* table) { return m->impl->run(params, prm, table); }
-int xee_series_get_field(xee_series* m, int which, void* out) { return m->impl->get_field(which, out); }
+int xee_series_destroy(xee_series* m) { if (m) { DeviceGuard g(m->impl->device()); delete m->impl; delete m; } return 0; }
+int xee_series_run_host(xee_series* m, const double* params, const xee_solve_params* prm, double* table) { DeviceGuard g(m->impl->device()); return m->impl->run(params, prm, table); }
+int xee_series_get_field(xee_series* m, int which, void* out) { DeviceGuard g(m->impl->device()); return m->impl->get_field(which, out); }
 int xee_series_sweep_kernel_stats(xee_series* m, double* ms, long long* launches, int reset) {
   PlanBase* p = m->impl->plan();
   if (ms) *ms = p->sweep_ms;

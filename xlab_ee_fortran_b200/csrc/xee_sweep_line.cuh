@@ -73,9 +73,21 @@ template <class T> struct Cfg {
   // float (8 floats = 2 chunks per thread, pitch AP = 17 chunks)
   static constexpr int AP = (TW + 4) * 4, A_BYTES = AP * TH;
   static constexpr int FAC_BYTES = 2 * F_BYTES + 2 * A_BYTES;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES;
+  // result staging for the TMA store (two buffers, same [TH][FW] layout as the f box: odd chunk pitch, conflict-free STS.128)
+  static constexpr int OUT_BYTES = F_BYTES, NOUT = 2;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES + NOUT * OUT_BYTES;
   static_assert((XW / V) % 2 == 1 && (FW / V) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
+// TMA store of one [1][TH][1][FW] box (4-D map: column-in-tile, tile column, row, solve) from shared memory; bulk async-group
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(smem_src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cta_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // 16-byte shared-memory load into V consecutive elements.
@@ -253,12 +265,14 @@ struct LineArgs {
   const int* done;
   double* partial;         // [n][ntiles] sum of r^2 (CHECK)
   int tiles_x, tiles_y, nchunks, chunk;
+  int tstore;              // 1: results leave through shared memory + TMA stores (needs nx % TW == 0); 0: 128-bit global stores
 };
 
 template <class T, bool CHEB, bool CHECK>
 __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
     sweep_line_kernel(const __grid_constant__ LineArgs<T> a, const __grid_constant__ CUtensorMap map_x,
-                      const __grid_constant__ CUtensorMap map_xm, const __grid_constant__ CUtensorMap map_f) {
+                      const __grid_constant__ CUtensorMap map_xm, const __grid_constant__ CUtensorMap map_f,
+                      const __grid_constant__ CUtensorMap map_out) {
   using namespace ln;
   using tma::mbar_init; using tma::mbar_expect_tx; using tma::mbar_wait; using tma::tma_load_3d;
   using C = Cfg<T>;
@@ -318,6 +332,8 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
   const uint32_t fofs = (uint32_t)(C::X_BYTES + r * C::FP + SEG * sg * C::ES);  // ... in the f box
   const uint32_t faca = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + r * C::FP + SEG * sg * C::ES);   // own cells of the factor planes m, u
   const uint32_t auxa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + 2 * C::F_BYTES + r * C::AP + SEG * sg * 4);   // ... v, w (float)
+  const uint32_t outa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + C::FAC_BYTES + r * C::FP + SEG * sg * C::ES);  // own cells of result buffer 0
+  const bool tstore = a.tstore != 0;
   uint32_t it = 0;
 
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -365,8 +381,18 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
         ldg16(pa + (size_t)(6 + q) * NT * 4, &cA[q * 4]);
       }
     }
+    // stop flags of this unit's solves (chunk <= 32) as one register mask: no shared-memory load per (tile, solve)
+    uint32_t umask = 0;
+    if (a.done != nullptr) {
+      if (done_in_smem) {
+        const int w0 = n0 >> 5;
+        umask = __funnelshift_r(sdone[w0], w0 + 1 < kDoneWords ? sdone[w0 + 1] : 0u, n0 & 31);
+      } else {
+        for (int n = n0; n < n1; ++n) umask |= (a.done[n] != 0 ? 1u : 0u) << (n - n0);
+      }
+    }
     for (int n = n0; n < n1; ++n) {
-      if (is_done(n)) continue;
+      if ((umask >> (n - n0)) & 1u) continue;
       const uint32_t s = it % NSTAGE;
       mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
       const uint32_t sb = sm0 + s * C::STAGE_BYTES;
@@ -458,16 +484,36 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
           for (int e = 0; e < SEG; ++e) out[e] = Rn<T>::fma(om, (x[e] - acc[e]) - xm[e], xm[e]);
         }
       }
-      cta_bar_sync();                           // every thread is done with the stage
-      if (tid == 0) issue_next();               // ... refill it, NSTAGE items ahead
-      T* const o = a.dst + ((size_t)n * nn + gofs);
-      if (seg_full) {
+      if (tstore) {
+        // results -> this iteration's staging buffer; made visible to the async proxy before the barrier.  Thread 0 first
+        // makes sure the previous TMA store has finished READING its buffer, which the next iteration overwrites.
+        const uint32_t ob = outa + (it & 1u) * C::OUT_BYTES;
 #pragma unroll
-        for (int q = 0; q < NV; ++q) stg16(o + q * V, &out[q * V]);
-      } else if (row_in) {
+        for (int q = 0; q < NV; ++q) sts16(ob + 16u * q, &out[q * V]);
+        fence_proxy_async_smem();
+        if (tid == 0) tma_store_wait_read0();
+      }
+      cta_bar_sync();                           // every thread is done with the stage (and has staged its results)
+      if (tid == 0) {
+        issue_next();                           // ... refill it, NSTAGE items ahead
+        if (tstore) {
+          // box [TH][FW] at (column 0 of tile column tile % tiles_x, row j0, solve n): columns >= TW and rows >= ny are out
+          // of bounds of the 4-D map and are not written
+          tma_store_4d(&map_out, sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + C::FAC_BYTES) + (it & 1u) * C::OUT_BYTES, 0,
+                       tile % a.tiles_x, j0, n);
+          tma_store_commit();
+        }
+      }
+      if (!tstore) {
+        T* const o = a.dst + ((size_t)n * nn + gofs);
+        if (seg_full) {
 #pragma unroll
-        for (int e = 0; e < SEG; ++e)
-          if (gi + e < a.nx) o[e] = out[e];
+          for (int q = 0; q < NV; ++q) stg16(o + q * V, &out[q * V]);
+        } else if (row_in) {
+#pragma unroll
+          for (int e = 0; e < SEG; ++e)
+            if (gi + e < a.nx) o[e] = out[e];
+        }
       }
       if (CHECK) {
 #pragma unroll
@@ -484,6 +530,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
       ++it;
     }
   }
+  if (tstore && tid == 0) tma_store_wait_all();   // the staging buffers must outlive the last stores
 }
 
 }  // namespace xee
