@@ -112,9 +112,10 @@ void xee_cal_uw_f64(const double* rpsi, double* u, double* w, const double* ra, 
 #define XEE_ARITH_FAST 1   /* FMA + precomputed reciprocal (same fixed point, 1e-13 rel) */
 #define XEE_METHOD_JACOBI 0    /* the reference's weighted Jacobi                        */
 #define XEE_METHOD_CHEBYSHEV 1 /* Chebyshev-accelerated Jacobi (same residual definition)*/
-/* Segment-line relaxation along the radius (not in the reference): same discrete problem, residual and stop rule, but
- * the correction solves coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i) exactly on segments of 8 radial points instead
- * of dividing r by coe5.  Shared operator, FAST arithmetic only. */
+/* Block-line relaxation along the radius (not in the reference): same discrete problem, residual and stop rule, but
+ * the correction solves coe4 z(i-1) + coe5 z(i) + coe6 z(i+1) = r(i) exactly on aligned BLOCKS OF 32 radial points
+ * (four 8-point thread segments coupled through a precomputed reduced system) instead of dividing r by coe5.
+ * Shared operator or one operator per solve; FAST arithmetic only; sweep kernel 5. */
 #define XEE_METHOD_LINE_JACOBI 2
 #define XEE_METHOD_LINE_CHEBYSHEV 3
 
@@ -172,8 +173,8 @@ void xee_release_cached_memory(void);
 long long xee_launch_count(int reset);
 /* Time (ms, CUDA events on the plan's stream) spent in the dominant sweep kernel and SWEEPS it performed since reset. */
 int xee_sweep_kernel_stats(xee_plan* p, double* ms_total, long long* sweeps, int reset);
-/* Sweep-kernel variant of the last solve (1 direct, 2 TMA pipeline, 3 resident, 4 temporal blocking), the sweeps one
- * launch of it performs (>1 only for variant 4) and its launches since the last stats reset. */
+/* Sweep-kernel variant of the last solve (1 direct, 2 TMA pipeline, 3 resident, 4 temporal blocking, 5 block-line), the
+ * sweeps one launch of it performs (>1 only for variant 4) and its launches since the last stats reset. */
 int xee_plan_kernel_info(xee_plan* p, int* variant, int* sweeps_per_pass, long long* kernel_launches);
 
 /* Post-processing on device fields (K5/K6), batch-wide.  geometry arrays are DEVICE pointers of the plan dtype. */
@@ -238,6 +239,9 @@ int xee_series_run_host(xee_series* s, const double* params_host, const xee_solv
 int xee_series_get_field(xee_series* s, int which, void* host_out);
 int xee_series_sweep_kernel_stats(xee_series* s, double* ms_total, long long* sweeps, int reset);
 int xee_series_kernel_info(xee_series* s, int* variant, int* sweeps_per_pass, long long* kernel_launches);
+/* Host wall time (ms) the spectral-radius probes of the accelerated methods have taken since the last reset (with one
+ * operator per solve they run once per run(): bench.py reports their share of a step). */
+int xee_series_probe_stats(xee_series* s, double* ms_total, int reset);
 
 #ifdef __cplusplus
 }

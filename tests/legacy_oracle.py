@@ -17,6 +17,27 @@ def old_solve(strategy, strategy_r, max_iter, alpha, dat, coe, f):
     return r["dat"], r["max_iter"], r["r1"]
 
 
+def exchange_conversion(rpsi, rchi, rhoC, g):
+    """cal_exchange_conversion (old-diagnose/diagnose.f90:1143-1174): the top/bottom boundary exchange term
+    (rhoC/rho) (psi d(chi)/dz - chi d(psi)/dz) / r^2 at the mid-points of the first and last row, and its integral
+    sum = -sum_i (top - bottom) r dr.  Deviation [D5]: r, dr, dz are REAL here (the legacy code declares them INTEGER,
+    :1146, which truncates r to whole metres and makes dz = za(2)-za(1) an integer).  Returns (bndconv [2][nr-1], sum)."""
+    ra, za, rho = g["ra"], g["za"], g["rho"]
+    dz = za[1] - za[0]; dr = ra[1] - ra[0]
+    r = (ra[:-1] + ra[1:]) / 2.0
+    pair = lambda x, j: x[j, :-1] + x[j, 1:]
+    def row(jb, jin, sign):     # jb = boundary row, jin = its inner neighbour; sign: +1 bottom (inner - boundary), top (boundary - inner)
+        dchi = sign * (pair(rchi, jin) - pair(rchi, jb)) / (2.0 * dz)
+        dpsi = sign * (pair(rpsi, jin) - pair(rpsi, jb)) / (2.0 * dz)
+        return (pair(rhoC, jb) / (2.0 * rho[jb])) * ((pair(rpsi, jb) / 2.0) * dchi - (pair(rchi, jb) / 2.0) * dpsi) / r ** 2.0
+    nz = rpsi.shape[0]
+    bottom = row(0, 1, 1.0); top = row(nz - 1, nz - 2, -1.0)
+    total = 0.0
+    for i in range(len(r)):                 # the reference accumulates sequentially (:1172)
+        total = total - (top[i] - bottom[i]) * r[i] * dr
+    return np.stack([bottom, top]), total
+
+
 def decompose(A, B, C, Q, F, Lr, Lz, testing_dt, rpsi_set, rchi_set, baro=2, rchi_bc=None, rpsi_bc=None, tendency=True):
     """rpsi_set / rchi_set = (strategy, strategy_r, max_iter, alpha).  Returns dict of sums and fields."""
     dt = np.float64
@@ -90,4 +111,13 @@ def decompose(A, B, C, Q, F, Lr, Lz, testing_dt, rpsi_set, rchi_set, baro=2, rch
         u, w = O.cal_uw(rpsi, d)
         out[f"rpsi_after_{tag}"] = rpsi
         out[f"sum_wtheta_{tag}"] = intB(O.cal_wtheta(w, theta, d)) * g0 / th0
+    if rchi_bc is not None:
+        # exchange conversion :730-772: the driver re-reads the float32 files it wrote, sums the chi fields in working precision
+        f32 = lambda x: np.asarray(x, np.float32).astype(dt)
+        for tag in ops:
+            psi_ = f32(out[f"rpsi_after_{tag}"])
+            chi3 = f32(out[f"rchi_{tag}_0"]) + f32(out[f"rchi_{tag}_dB"]) + f32(out[f"rchi_{tag}_B0"])
+            chi2 = f32(out[f"rchi_{tag}_dB"]) + f32(out[f"rchi_{tag}_B0"])
+            out[f"bndconv_{tag}"], out[f"sum_bndconv_{tag}"] = exchange_conversion(psi_, chi3, C, g)      # method 1
+            out[f"bndconv2_{tag}"], out[f"sum_bndconv2_{tag}"] = exchange_conversion(psi_, chi2, C, g)    # method 2
     return out

@@ -109,15 +109,18 @@ def test_full_size_map_shard_properties(method):
     Lp = plan.apply(torch.from_numpy(psi2[idx]).cuda()).cpu().numpy()
     res = np.sqrt(((Lp - 2.0 * f[idx])[:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2)))
     assert np.all(res <= 4e-12 * np.sqrt(((2.0 * f[idx])[:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2))))
-    # the reference's own iteration on two of the locations
-    mj = EfficiencyMap(A, B, C, Lr, Lz, 2, "f64", arith="strict", method="jacobi", r1_rel=1e-12)
-    tj = mj.run(heat[[3, 77]], X.SolveParams(max_iter=5000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=3))
+    # the reference's own iteration on two of the locations.  The comparison solve is iterated FURTHER than the bench
+    # tolerance (r1 = 1e-13 rms(f), or to its round-off floor: err 4): Jacobi stopped at 1e-12 rms(f) still carries
+    # ~(1/(1-rho)) 1e-12 = 3e-8 of its slowest mode, which would hide whether the accelerated solve meets the north_star
+    # bound.  Against the tighter reference solve the accelerated fields must be within 1e-8 relative L2.
+    mj = EfficiencyMap(A, B, C, Lr, Lz, 2, "f64", arith="strict", method="jacobi", r1_rel=1e-13)
+    tj = mj.run(heat[[3, 77]], X.SolveParams(max_iter=8000000, check_step=100, converge_time=2, r1=1.0, r2=0.0, sync_every=3,
+                                             stall_checks=40))
     pj = mj.field("psi")
-    assert np.all(tj[:, 2] == 0) and np.all(tj[:, 0] > 50 * tab[[3, 77], 0])
-    # Two different iterations stopped at the same residual r1 = 1e-12*rms(f) agree to ~(1/(1-rho))*1e-12 = 3e-8 at
-    # worst (Jacobi's remaining error sits in the slowest mode); the fp64 round-off floor (~1e-12) forbids a tighter
-    # common tolerance at 512x256.  Same-iteration parity (STRICT Jacobi vs the oracle) is bit-exact elsewhere.
-    assert rel_l2(pj[0], psi[3]) < 5e-8 and rel_l2(pj[1], psi[77]) < 5e-8
+    assert np.all((tj[:, 2] == 0) | (tj[:, 2] == 4)) and np.all(tj[:, 0] > 50 * tab[[3, 77], 0])
+    assert np.all(tj[:, 1] <= 1e-12 * np.sqrt((f[[3, 77]][:, 1:-1, 1:-1] ** 2).mean(axis=(1, 2))))   # at least the bench tolerance
+    print("accelerated vs reference iteration, rel L2:", rel_l2(pj[0], psi[3]), rel_l2(pj[1], psi[77]), "Jacobi sweeps", tj[:, 0])
+    assert rel_l2(pj[0], psi[3]) < 1e-8 and rel_l2(pj[1], psi[77]) < 1e-8          # north_star: streamfunction within 1e-8
     assert np.allclose(tj[:, 5], tab[[3, 77], 5], rtol=1e-6)              # efficiency within 1e-6 relative
 
 

@@ -83,3 +83,27 @@ def test_series_exact_chain_on_identical_inputs():
         assert np.array_equal(ts.field("theta")[n], background_theta(A[n], B[n], C[n], d, dt))
         ke = O.integrate_weight_B(O.cal_wtheta(w, ts.field("theta")[n], d), d) * float(k["g0"]) / float(k["theta0"])
         assert tab[n, 4] == pytest.approx(ke, rel=1e-9)
+
+
+def test_series_sharded_equals_unsharded():
+    """time_series.run_sharded (BASELINE config 5 over several GPUs): the concatenated per-rank tables are the table of
+    the whole series run in one piece (independent solves: identical sweep counts and fields' scalars)."""
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.time_series import TimeSeries, run_sharded
+    nr, nz, total = 64, 48, 7
+    Lr, Lz = (0.0, 6.0e5), (0.0, 1.5e4)
+    prm = X.SolveParams(max_iter=400000, check_step=25, converge_time=2, r1=1.0, r2=0.0, stall_checks=20)
+    kw = dict(dtype="f64", arith="fast", method="line_chebyshev", r1_rel=1e-10)
+    ts = TimeSeries(nr, nz, Lr, Lz, total, **kw)
+    whole = ts.run(W.series_params(total), prm)
+    assert ts.kernel_info()[0] == 5 and ts.probe_ms() > 0.0
+    ts.close()
+    parts = []
+    for rank in range(3):
+        a, b, tab = run_sharded(nr, nz, Lr, Lz, total, prm, world=3, rank=rank, **kw)
+        assert tab.shape == (b - a, 8)
+        parts.append(tab)
+    got = np.concatenate(parts)
+    assert np.all(got[:, 2] == 0) and np.array_equal(got[:, 0], whole[:, 0])
+    assert np.allclose(got[:, 3:], whole[:, 3:], rtol=1e-9, atol=0)

@@ -96,7 +96,10 @@ struct DevPool {
       if (it != free_blocks.end()) { *out = it->second; cached -= bytes; free_blocks.erase(it); live[*out] = key; return cudaSuccess; }
     }
     cudaError_t e = cudaMalloc(out, bytes);
-    if (e != cudaSuccess) { trim(0); e = cudaMalloc(out, bytes); }
+    if (e != cudaSuccess) {
+      cudaGetLastError();   // clear the sticky-free allocation error: the retry below may succeed and the next launch check must not see it
+      trim(0); e = cudaMalloc(out, bytes);
+    }
     if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = key; }
     return e;
   }
@@ -142,6 +145,7 @@ struct PlanBase {
   virtual int apply(const void* psi, void* out, cudaStream_t s) = 0;
   virtual int coe_to_aos_host(void* coe_host) = 0;
   double sweep_ms = 0.0;
+  double probe_ms = 0.0;             // host wall time spent in the spectral-radius probes (estimate_rho)
   long long sweep_launches = 0;      // sweeps performed (v4 does up to tb_depth of them per kernel launch)
   long long kernel_launches = 0;     // launches of the sweep kernel
   int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..4) and its sweeps per pass
@@ -396,6 +400,9 @@ struct Plan : PlanBase {
     return 0;
   }
   ~Plan() override {
+    // The pool recycles blocks without stream tracking: make sure no kernel of this plan (or of a caller's stream that used
+    // its buffers: apply / eta / uw return without synchronising) still touches them before they go back on the free list.
+    cudaDeviceSynchronize();
     { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
@@ -692,7 +699,11 @@ struct Plan : PlanBase {
       return 0;
     }
     if (cheb_rho > 0 && (int)rho_ps.size() == nsets) return 0;
-    return estimate_rho(s);
+    XEE_CHECK(cudaStreamSynchronize(s));
+    const double t0 = TraceTimer::now();
+    const int rc = estimate_rho(s);      // synchronises the stream before it returns
+    probe_ms += (TraceTimer::now() - t0) * 1e3;
+    return rc;
   }
 
   int sweeps(void* psi, const void* f, double alpha, int nsw, double* rms, cudaStream_t s) override {
@@ -729,9 +740,9 @@ struct Plan : PlanBase {
     }
     XEE_CHECK(cudaMemcpyAsync(x1, x0, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     if (prepare_maps(x0, x1, (const T*)f, d.nbatch)) return 1;
+    if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;   // before the start event: the spectral probe is not sweep time
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
-    if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;
     for (int cnt = 1; cnt <= nsw; ++cnt) {
       const T* src = (cnt & 1) ? x0 : x1;
       T* dst = (cnt & 1) ? x1 : x0;
@@ -778,6 +789,11 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   //            x1 = rho_1/rho_E, xE = 1/rho_E.  Repeated until the correction is below 2 % of 1 - rho.
   const int ns = nsets;
   T *e0 = nullptr, *e1 = nullptr, *zf = nullptr; double* nrm_d = nullptr;
+  // the probe changes the launch geometry (nbatch, gz, spb): restored, and the probe buffers freed, on every exit path
+  struct Restore {
+    Plan<T>* p; int nb, gz, spb; T **e0, **e1, **zf; double** nrm;
+    ~Restore() { p->d.nbatch = nb; p->gz = gz; p->spb = spb; pool_free(*e0); pool_free(*e1); pool_free(*zf); pool_free(*nrm); }
+  } restore{this, d.nbatch, gz, spb, &e0, &e1, &zf, &nrm_d};
   XEE_CHECK(pool_alloc(&e0, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&e1, sizeof(T) * nn * ns));
   XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&nrm_d, sizeof(double) * ns));
   if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * ns));
@@ -789,7 +805,6 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
   XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
   // probe launch geometry: `ns` solves through the direct kernel
-  const int save_nb = d.nbatch, save_gz = gz, save_spb = spb;
   d.nbatch = ns; spb = 1; gz = ns;
   std::vector<double> nA(ns), nB(ns), rho(ns, 0.0);
   std::vector<T> rho_h(ns);
@@ -860,8 +875,6 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     }
     if (all_settled) break;
   }
-  d.nbatch = save_nb; gz = save_gz; spb = save_spb;
-  pool_free(e0); pool_free(e1); pool_free(zf); pool_free(nrm_d);
   if (rc) return 1;
   rho_ps = rho;
   for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];

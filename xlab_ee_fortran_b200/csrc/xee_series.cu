@@ -295,6 +295,12 @@ int xee_series_sweep_kernel_stats(xee_series* m, double* ms, long long* launches
   if (reset) { p->sweep_ms = 0; p->sweep_launches = 0; p->kernel_launches = 0; }
   return 0;
 }
+int xee_series_probe_stats(xee_series* m, double* ms, int reset) {
+  PlanBase* p = m->impl->plan();
+  if (ms) *ms = p->probe_ms;
+  if (reset) p->probe_ms = 0;
+  return 0;
+}
 int xee_series_kernel_info(xee_series* m, int* variant, int* sweeps_per_pass, long long* kernel_launches) {
   PlanBase* p = m->impl->plan();
   if (variant) *variant = p->variant_used;

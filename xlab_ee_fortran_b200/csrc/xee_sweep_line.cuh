@@ -348,6 +348,20 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
 #pragma unroll
     for (int e = 0; e < SEG; ++e)
       if (gi + e >= 1 && gi + e < a.nx - 1 && gj >= 1 && gj < a.ny - 1) inb |= 1u << e;
+    // stop flags of this unit's solves (chunk <= 32) as one register mask: no shared-memory load per (tile, solve)
+    uint32_t umask = 0;
+    if (a.done != nullptr) {
+      if (done_in_smem) {
+        const int w0 = n0 >> 5;
+        umask = __funnelshift_r(sdone[w0], w0 + 1 < kDoneWords ? sdone[w0 + 1] : 0u, n0 & 31);
+      } else {
+        for (int n = n0; n < n1; ++n) umask |= (a.done[n] != 0 ? 1u : 0u) << (n - n0);
+      }
+    }
+    {
+      const uint32_t full = n1 - n0 >= 32 ? 0xffffffffu : (1u << (n1 - n0)) - 1u;
+      if ((umask & full) == full) continue;   // every solve of the unit has stopped: skip it before reloading the operator
+    }
     // the 9 coefficients of the thread's points and its 2 x 8 reduced-system coefficients (float) stay in registers for the
     // whole chunk; the factors m, u, v, w go to thread-private cells of shared memory (read back by the same thread only)
     T cf[9][SEG];
@@ -379,16 +393,6 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
       for (int q = 0; q < 2; ++q) {
         ldg16(pa + (size_t)(4 + q) * NT * 4, &cB[q * 4]);
         ldg16(pa + (size_t)(6 + q) * NT * 4, &cA[q * 4]);
-      }
-    }
-    // stop flags of this unit's solves (chunk <= 32) as one register mask: no shared-memory load per (tile, solve)
-    uint32_t umask = 0;
-    if (a.done != nullptr) {
-      if (done_in_smem) {
-        const int w0 = n0 >> 5;
-        umask = __funnelshift_r(sdone[w0], w0 + 1 < kDoneWords ? sdone[w0 + 1] : 0u, n0 & 31);
-      } else {
-        for (int n = n0; n < n1; ++n) umask |= (a.done[n] != 0 ? 1u : 0u) << (n - n0);
       }
     }
     for (int n = n0; n < n1; ++n) {

@@ -88,7 +88,7 @@ class EfficiencyMap:
         return ms.value, n.value
 
     def kernel_info(self):
-        """(variant 1..4, sweeps per kernel launch, kernel launches since the last stats reset) of the sweep kernel."""
+        """(variant 1..5, sweeps per kernel launch, kernel launches since the last stats reset) of the sweep kernel."""
         v = C.c_int(0); d = C.c_int(0); n = C.c_longlong(0)
         _lib.lib().xee_map_kernel_info(self._h, C.byref(v), C.byref(d), C.byref(n))
         return v.value, d.value, n.value

@@ -58,4 +58,32 @@ class TimeSeries:
     def sweep_kernel_stats(self, reset=False):
         ms = C.c_double(0); n = C.c_longlong(0)
         _lib.lib().xee_series_sweep_kernel_stats(self._h, C.byref(ms), C.byref(n), C.c_int(int(reset)))
+        if reset:
+            _lib.lib().xee_series_probe_stats(self._h, None, C.c_int(1))
         return ms.value, n.value
+
+    def probe_ms(self):
+        """Host wall time (ms) of the spectral-radius probes since the last stats reset."""
+        ms = C.c_double(0)
+        _lib.lib().xee_series_probe_stats(self._h, C.byref(ms), C.c_int(0))
+        return ms.value
+
+    def kernel_info(self):
+        """(variant 1..5, sweeps per kernel launch, kernel launches since the last stats reset) of the sweep kernel."""
+        v = C.c_int(0); d = C.c_int(0); n = C.c_longlong(0)
+        _lib.lib().xee_series_kernel_info(self._h, C.byref(v), C.byref(d), C.byref(n))
+        return v.value, d.value, n.value
+
+
+def run_sharded(nr, nz, Lr, Lz, total, p: SolveParams, world=1, rank=0, device=-1, **kw):
+    """BASELINE config 5 on `world` GPUs: snapshots [a, b) of a `total`-long series on this rank (static contiguous chunks,
+    SURVEY section 8e: independent solves, nothing exchanged), parameters generated per rank from the snapshot index.
+    Returns (a, b, table [b-a, 8]); gather the rows with efficiency_map.gather_rows (one collective)."""
+    from . import workloads as W
+    from .efficiency_map import partition
+    a, b = partition(total, world, rank)
+    ts = TimeSeries(nr, nz, Lr, Lz, b - a, device=device, **kw)
+    try:
+        return a, b, ts.run(W.series_params(b - a, total=total, first=a), p)
+    finally:
+        ts.close()
