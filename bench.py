@@ -318,6 +318,8 @@ def run_ours(args):
     interior = (NR - 2) * (NZ - 2)
     cheb = args.method.endswith("chebyshev"); line = args.method.startswith("line")
     fields = 4 if cheb else 3                                      # psi read, psi write, f read (+ psi_{k-1} for Chebyshev)
+    if args.method.startswith("line2"):
+        fields += 2                                                # + the prolongation pass of the coarse correction (psi read + write)
     opw = (13 if line else 9)                                      # operator words per point: 9 coefficients (+ m, u and 4 float planes)
     b_alg = 8.0 * (fields + (opw if series else opw / nloc))       # one operator per solve: it streams with every sweep
     alg_bytes = float(tab[:, 0].sum()) * interior * b_alg * args.steps
@@ -450,10 +452,11 @@ def main():
     ap.add_argument("--nheat", type=int, default=512, help="map: heating locations (independent solves) per GPU")
     ap.add_argument("--nsnap", type=int, default=128, help="series: snapshots (independent solves, one operator each) per GPU")
     ap.add_argument("--total", type=int, default=0, help="fix the TOTAL number of locations / snapshots (strong scaling); 0 = per-GPU count x GPUs")
-    ap.add_argument("--method", default="line_chebyshev", choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi"])
+    ap.add_argument("--method", default="line_chebyshev", choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi", "line2_chebyshev"])
     ap.add_argument("--check-step", type=int, default=0,
                     help="sweeps between residual checks (solve_elliptic's check_step); 0 = 100 for the point methods, 25 for the "
-                         "line methods, which need ~4x fewer sweeps (a solve stops at the 2nd consecutive check below r1)")
+                         "line methods, which need ~4x fewer sweeps, 10 for the two-level method (a solve stops at the 2nd consecutive "
+                         "check below r1)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--max-iter", type=int, default=2000000)
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -462,7 +465,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.check_step <= 0:
-        args.check_step = 25 if args.method.startswith("line") else 100
+        args.check_step = 10 if args.method.startswith("line2") else 25 if args.method.startswith("line") else 100
     args.per_gpu = args.nsnap if args.workload == "series" else args.nheat
     if args.total > 0:
         args.per_gpu = (args.total + max(args.gpus, 1) - 1) // max(args.gpus, 1)

@@ -118,6 +118,11 @@ void xee_cal_uw_f64(const double* rpsi, double* u, double* w, const double* ra, 
  * Shared operator or one operator per solve; FAST arithmetic only; sweep kernel 5. */
 #define XEE_METHOD_LINE_JACOBI 2
 #define XEE_METHOD_LINE_CHEBYSHEV 3
+/* Two-level block-line relaxation (not in the reference): the block-line correction PLUS a coarse-grid correction
+ * P Ac^-1 P^T r (bilinear coarse space, nodes every 16 grid points, Galerkin Ac = P^T L P inverted once per operator);
+ * same discrete problem, residual and stop rule.  Shared operator, FAST arithmetic, grids of at least 34 x 34 points. */
+#define XEE_METHOD_LINE2_JACOBI 4
+#define XEE_METHOD_LINE2_CHEBYSHEV 5
 
 typedef struct xee_plan xee_plan;
 
@@ -176,6 +181,9 @@ int xee_sweep_kernel_stats(xee_plan* p, double* ms_total, long long* sweeps, int
 /* Sweep-kernel variant of the last solve (1 direct, 2 TMA pipeline, 3 resident, 4 temporal blocking, 5 block-line), the
  * sweeps one launch of it performs (>1 only for variant 4) and its launches since the last stats reset. */
 int xee_plan_kernel_info(xee_plan* p, int* variant, int* sweeps_per_pass, long long* kernel_launches);
+/* Chebyshev parameters in use (after a solve / sweeps call of an accelerated method): spectral radius rho of the iteration
+ * matrix I - gamma M^-1 L and the step length gamma (1 for the one-level methods). */
+int xee_plan_cheb_params(xee_plan* p, double* rho, double* gamma);
 
 /* Post-processing on device fields (K5/K6), batch-wide.  geometry arrays are DEVICE pointers of the plan dtype. */
 int xee_eta_dev(int dtype, const void* rchi, void* eta, const void* ra, const void* rcuva, const void* rho,

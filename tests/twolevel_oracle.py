@@ -6,7 +6,8 @@ xtt-lib-fortran/elliptic_tools.f90:77-85, minus f) becomes
 
 with M the 32-point radial block systems of tests/line_oracle.py, P bilinear interpolation from a coarse grid with
 nodes every (AX, AZ) grid points (Dirichlet boundary: no nodes on it) and Ac = P^T L P the Galerkin coarse operator.
-Not in the reference and not in the CUDA library yet: this file pins the formulation the next round builds.
+Not in the reference.  The CUDA library implements it as XEE_METHOD_LINE2_* (csrc/xee_twolevel.cuh, nodes every 16 x 16 grid
+points); tests/test_gpu_twolevel.py compares the kernels with this restatement sweep by sweep.
 """
 import numpy as np
 
@@ -24,7 +25,7 @@ def hat(n, step):
 
 
 class TwoLevel:
-    def __init__(self, coe, ax=32, az=8):
+    def __init__(self, coe, ax=16, az=16):
         self.coe = coe.astype(np.float64)
         ny, nx = coe.shape[:2]
         self.Px, self.Pz = hat(nx, ax), hat(ny, az)            # P = Pz (x) Px, applied as Pz @ C @ Px^T
@@ -71,6 +72,18 @@ class TwoLevel:
             xj = x - alpha * self.correction(r)
             x, xm = om * (xj - xm) + xm, x
         return x, max_sweeps
+
+    def chebyshev_sweeps(self, x0, f, gamma, rho, sweeps):
+        """Exactly `sweeps` Chebyshev sweeps with step gamma and spectral radius rho (the values the library reports through
+        xee_plan_cheb_params); the weights in the closed form of cheb_omega (csrc/xee_kernels.cuh)."""
+        x = x0.copy(); xm = x0.copy()
+        sg = 1.0 / rho; q = sg - np.sqrt(sg * sg - 1.0)
+        for k in range(1, sweeps + 1):
+            om = 1.0 if k == 1 else (2.0 / rho) * q * (1.0 + q ** (2 * (k - 1))) / (1.0 + q ** (2 * (k - 1)) * q * q)
+            r = LO.residual(x, self.coe, f)
+            xj = x - gamma * self.correction(r)
+            x, xm = om * (xj - xm) + xm, x
+        return x
 
     def spectral_radius(self, alpha, iters=400):
         ny, nx = self.coe.shape[:2]

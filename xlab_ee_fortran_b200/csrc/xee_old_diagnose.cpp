@@ -384,13 +384,22 @@ int run() {
       read_field(output_folder + "/rpsi_after-[0]-O.bin", psi_, nO); read_field(output_folder + "/rchi-[0_0]-O.bin", chi_, nO);
       add_from(output_folder + "/rchi-[0_dB]-O.bin"); add_from(output_folder + "/rchi-[0_B0]-O.bin");
       exchange(psi_, chi_, bnd, sBnd_0); write_field(output_folder + "/bndconv-[0].bin", bnd, bnd.size());
-      read_field(output_folder + "/rchi-[0_dB]-O.bin", chi_, nO); add_from(output_folder + "/rchi-[0_B0]-O.bin");
-      exchange(psi_, chi_, bnd, sBnd2_0); write_field(output_folder + "/bndconv2-[0].bin", bnd, bnd.size());
     }
     if (baro1) {
       read_field(output_folder + "/rpsi_after-[B0dB]-O.bin", psi_, nO); read_field(output_folder + "/rchi-[B0dB_0]-O.bin", chi_, nO);
       add_from(output_folder + "/rchi-[B0dB_dB]-O.bin"); add_from(output_folder + "/rchi-[B0dB_B0]-O.bin");
       exchange(psi_, chi_, bnd, sBnd_B); write_field(output_folder + "/bndconv-[B0dB].bin", bnd, bnd.size());
+    }
+    // Boundary conversion method 2 (:753-772): the same term without the boundary-condition chi; the reference prints the
+    // same message again
+    std::printf(" Exchange conversion term check...\n");
+    if (baro0) {
+      read_field(output_folder + "/rpsi_after-[0]-O.bin", psi_, nO);
+      read_field(output_folder + "/rchi-[0_dB]-O.bin", chi_, nO); add_from(output_folder + "/rchi-[0_B0]-O.bin");
+      exchange(psi_, chi_, bnd, sBnd2_0); write_field(output_folder + "/bndconv2-[0].bin", bnd, bnd.size());
+    }
+    if (baro1) {
+      read_field(output_folder + "/rpsi_after-[B0dB]-O.bin", psi_, nO);
       read_field(output_folder + "/rchi-[B0dB_dB]-O.bin", chi_, nO); add_from(output_folder + "/rchi-[B0dB_B0]-O.bin");
       exchange(psi_, chi_, bnd, sBnd2_B); write_field(output_folder + "/bndconv2-[B0dB].bin", bnd, bnd.size());
     }

@@ -16,6 +16,7 @@
 #include "xee_sweep_tma.cuh"
 #include "xee_sweep_tb.cuh"
 #include "xee_sweep_line.cuh"
+#include "xee_twolevel.cuh"
 #include "xee_resident.cuh"
 
 namespace xee {
@@ -148,7 +149,8 @@ struct PlanBase {
   double probe_ms = 0.0;             // host wall time spent in the spectral-radius probes (estimate_rho)
   long long sweep_launches = 0;      // sweeps performed (v4 does up to tb_depth of them per kernel launch)
   long long kernel_launches = 0;     // launches of the sweep kernel
-  int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..4) and its sweeps per pass
+  int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..5) and its sweeps per pass
+  double cheb_rho_used = 0.0, cheb_gamma_used = 1.0;   // Chebyshev parameters of the last accelerated call
 };
 
 template <class T>
@@ -185,7 +187,15 @@ struct Plan : PlanBase {
   struct LineMap { const void* ptr; int nb; int kind; CUtensorMap map; };
   std::vector<LineMap> line_maps;    // kind 0: psi box (with halo), 1: f / psi_{k-1} box, 2: 4-D store view of the result
   bool ln_tstore = false;            // results leave through TMA stores (nx a multiple of the tile width)
-  bool method_is_cheb() const { return d.method == XEE_METHOD_CHEBYSHEV || d.method == XEE_METHOD_LINE_CHEBYSHEV; }
+  bool method_is_cheb() const { return d.method == XEE_METHOD_CHEBYSHEV || d.method == XEE_METHOD_LINE_CHEBYSHEV || d.method == XEE_METHOD_LINE2_CHEBYSHEV; }
+  // two-level block-line methods (XEE_METHOD_LINE2_*, xee_twolevel.cuh): coarse-grid data of the operator and of a batch
+  bool use_two = false;
+  tl::Dims tld{};
+  double *tl_ainv = nullptr, *tl_tmp = nullptr;   // [ncp][ncp]: Ac^-1 (and the second Gauss-Jordan buffer)
+  double *tl_part = nullptr;                      // [nbatch][ntiles][32] per-tile restriction of the residual
+  double *tl_rc = nullptr, *tl_cv = nullptr;      // [nbatch][ncp] restricted residual, [nbatch][pz][px] coarse correction
+  double tl_gamma = 1.0, tl_lmax = 0.0, tl_lmin = 0.0;
+  bool tl_ready = false;
   // v4 (temporal blocking) sweep kernel: two more iterate buffers (passes cannot update in place), tiling, maps
   bool use_tb = false;
   int tb_depth = 4, tb_tiles_x = 0, tb_tiles_y = 0, tb_chunk = 1, tb_nchunks = 1, tb_grid = 1;
@@ -259,8 +269,9 @@ struct Plan : PlanBase {
       if (nt > ntiles) return fail("xee: internal: partial buffer too small for the TMA tiling");
     }
     // v5: segment-line relaxation is a METHOD, not a variant of the reference iteration: explicit request only.
-    use_line = d.method == XEE_METHOD_LINE_JACOBI || d.method == XEE_METHOD_LINE_CHEBYSHEV;
-    if (d.method < 0 || d.method > XEE_METHOD_LINE_CHEBYSHEV) return fail("xee: unknown method");
+    use_two = d.method == XEE_METHOD_LINE2_JACOBI || d.method == XEE_METHOD_LINE2_CHEBYSHEV;
+    use_line = use_two || d.method == XEE_METHOD_LINE_JACOBI || d.method == XEE_METHOD_LINE_CHEBYSHEV;
+    if (d.method < 0 || d.method > XEE_METHOD_LINE2_CHEBYSHEV) return fail("xee: unknown method");
     if (use_line) {
       if (d.arith != XEE_ARITH_FAST || !tma_ok)
         return fail("xee: the line-relaxation methods need FAST arithmetic and nx*sizeof(real) % 16 == 0");
@@ -286,6 +297,19 @@ struct Plan : PlanBase {
       XEE_CHECK(pool_alloc(&linefac, sizeof(T) * kLineFacPlanes * nn * nsets));
       XEE_CHECK(pool_alloc(&linepack, (size_t)nt * line_pack_tile_bytes<T>() * nsets));
       want = 5;
+      if (use_two) {
+        static_assert(ln::TH == tl::HZ && 2 * ln::SEG == tl::HR, "the two-level restriction assumes 16-row tiles and two 8-point segments per coarse cell");
+        if (!d.shared_coe) return fail("xee: the two-level methods need a shared operator");
+        tld = tl::dims(d.nx, d.ny);
+        if (tld.ncx < 1 || tld.ncz < 1) return fail("xee: the two-level methods need at least 18 x 18 grid points (one coarse node)");
+        const size_t ab = sizeof(double) * (size_t)tld.ncp * tld.ncp;
+        XEE_CHECK(pool_alloc(&tl_ainv, ab)); XEE_CHECK(pool_alloc(&tl_tmp, ab));
+        XEE_CHECK(pool_alloc(&tl_part, sizeof(double) * (size_t)nb * nt * 32));
+        XEE_CHECK(pool_alloc(&tl_rc, sizeof(double) * (size_t)nb * tld.ncp));
+        XEE_CHECK(pool_alloc(&tl_cv, sizeof(double) * (size_t)nb * tld.pz * tld.px));
+        XEE_CHECK(cudaMemsetAsync(tl_rc, 0, sizeof(double) * (size_t)nb * tld.ncp, own_stream));                 // padding stays 0
+        XEE_CHECK(cudaMemsetAsync(tl_cv, 0, sizeof(double) * (size_t)nb * tld.pz * tld.px, own_stream));         // rim stays 0
+      }
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
     // divisions, where the redundant halo work of overlapping tiles costs more than the saved traffic).
@@ -403,7 +427,7 @@ struct Plan : PlanBase {
     // The pool recycles blocks without stream tracking: make sure no kernel of this plan (or of a caller's stream that used
     // its buffers: apply / eta / uw return without synchronising) still touches them before they go back on the free list.
     cudaDeviceSynchronize();
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_cv); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -456,6 +480,43 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     linefac_ready = true;
+    return use_two ? two_setup() : 0;
+  }
+  // Two-level methods, once per operator: Galerkin coarse operator Ac = P^T L P and its inverse (Gauss-Jordan on the device,
+  // one launch per pivot between two buffers).
+  int two_setup() {
+    TraceTimer tt("two-level setup");
+    const int nc = tld.nc, ncp = tld.ncp;
+    const size_t ab = sizeof(double) * (size_t)ncp * ncp;
+    XEE_CHECK(cudaMemsetAsync(tl_ainv, 0, ab, own_stream));
+    tl::galerkin_kernel<T><<<nc, 256, 0, own_stream>>>(coe, tl_ainv, d.nx, d.ny, tld.ncx, tld.ncz, ncp);
+    XEE_LAUNCH_OK();
+    if (ncp > nc) { tl::pad_identity_kernel<<<(ncp - nc + 63) / 64, 64, 0, own_stream>>>(tl_ainv, nc, ncp); XEE_LAUNCH_OK(); }
+    XEE_CHECK(cudaMemcpyAsync(tl_tmp, tl_ainv, ab, cudaMemcpyDeviceToDevice, own_stream));
+    double *src = tl_ainv, *dst = tl_tmp;
+    const dim3 g((nc + 127) / 128, nc);
+    for (int k = 0; k < nc; ++k) {
+      tl::gj_step_kernel<<<g, 128, 0, own_stream>>>(src, dst, nc, ncp, k);
+      std::swap(src, dst);
+    }
+    g_launches.fetch_add(nc, std::memory_order_relaxed);
+    XEE_CHECK(cudaGetLastError());
+    if (src != tl_ainv) XEE_CHECK(cudaMemcpyAsync(tl_ainv, src, ab, cudaMemcpyDeviceToDevice, own_stream));
+    XEE_CHECK(cudaStreamSynchronize(own_stream));
+    tl_ready = true; tl_lmax = tl_lmin = 0.0; tl_gamma = 1.0;
+    return 0;
+  }
+  // Coarse half of one two-level sweep, after the sweep kernel has left P^T r per tile: gather, dense coarse solve for the
+  // batch (scaled by `scale` = -omega gamma), prolongation added to the new iterate.
+  int two_coarse(T* xnew, int nb, double scale, const int* done, cudaStream_t s) {
+    const int nt = ln_tiles_x * ln_tiles_y;
+    tl::coarse_gather_kernel<<<nb, 256, 0, s>>>(tl_part, tl_rc, done, nt, ln_tiles_x, ln_tiles_y, tld.ncx, tld.ncz, tld.ncp);
+    XEE_LAUNCH_OK();
+    tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 256, 0, s>>>(tl_ainv, tl_rc, tl_cv, done, scale, nb, tld.nc, tld.ncp,
+                                                                                         tld.ncx, tld.px, tld.pz * tld.px);
+    XEE_LAUNCH_OK();
+    tl::prolong_add_kernel<T><<<dim3((d.nx + 255) / 256, d.ny, nb), 128, 0, s>>>(xnew, tl_cv, done, d.nx, d.ny, tld.px, tld.pz * tld.px);
+    XEE_LAUNCH_OK();
     return 0;
   }
   int coe_to_aos_host(void* coe_host) override {  // set 0 only (Fortran-facing cal_coe)
@@ -534,12 +595,17 @@ struct Plan : PlanBase {
     *out = lm.map;
     return 0;
   }
+  template <bool CHEB, bool CHECK, bool TWO>
+  int launch_line_inst2(const LineArgs<T>& A, int grid, const CUtensorMap& mx, const CUtensorMap& mxm, const CUtensorMap& mf, const CUtensorMap& mo, cudaStream_t s) {
+    constexpr int smem = TWO ? ln::Cfg<T>::SMEM_BYTES_TWO : ln::Cfg<T>::SMEM_BYTES;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (opt_in_smem(sweep_line_kernel<T, CHEB, CHECK, TWO>, smem, attr_done)) return 1;
+    sweep_line_kernel<T, CHEB, CHECK, TWO><<<grid, ln::NT, smem, s>>>(A, mx, mxm, mf, mo);
+    return 0;
+  }
   template <bool CHEB, bool CHECK>
   int launch_line_inst(const LineArgs<T>& A, int grid, const CUtensorMap& mx, const CUtensorMap& mxm, const CUtensorMap& mf, const CUtensorMap& mo, cudaStream_t s) {
-    static std::atomic<unsigned long long> attr_done{0};
-    if (opt_in_smem(sweep_line_kernel<T, CHEB, CHECK>, ln::Cfg<T>::SMEM_BYTES, attr_done)) return 1;
-    sweep_line_kernel<T, CHEB, CHECK><<<grid, ln::NT, ln::Cfg<T>::SMEM_BYTES, s>>>(A, mx, mxm, mf, mo);
-    return 0;
+    return use_two ? launch_line_inst2<CHEB, CHECK, true>(A, grid, mx, mxm, mf, mo, s) : launch_line_inst2<CHEB, CHECK, false>(A, grid, mx, mxm, mf, mo, s);
   }
   int launch_sweep_line(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
     if (!linefac_ready) return fail("xee: line relaxation: the operator has not been set");
@@ -553,12 +619,18 @@ struct Plan : PlanBase {
     A.tiles_x = ln_tiles_x; A.tiles_y = ln_tiles_y;
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
     A.tstore = ln_tstore ? 1 : 0;
+    A.gamma = (T)(use_two ? tl_gamma : 1.0); A.cpart = tl_part;
+    if (use_two && !tl_ready) return fail("xee: two-level method: the operator has not been set");
     const int grid = (int)std::min<long long>((long long)num_sms * ln::CTAS_PER_SM, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
     int rc;
     if (mode == MODE_CHEBYSHEV) rc = check ? launch_line_inst<true, true>(A, grid, cx, cxm, cf, co, s) : launch_line_inst<true, false>(A, grid, cx, cxm, cf, co, s);
     else rc = check ? launch_line_inst<false, true>(A, grid, cx, cxm, cf, co, s) : launch_line_inst<false, false>(A, grid, cx, cxm, cf, co, s);
     if (rc) return rc;
     XEE_LAUNCH_OK();
+    if (use_two) {   // psi' = psi - alpha (z + P E) (Jacobi) / y - omega gamma P E (Chebyshev; omega from the per-launch value)
+      const double scale = mode == MODE_CHEBYSHEV ? -(double)a.omega * tl_gamma : -(double)a.alpha;
+      return two_coarse(a.dst, a.nbatch, scale, a.done, s);
+    }
     return 0;
   }
   int launch_sweep(const SweepArgs<T>& a, int mode, bool check, cudaStream_t s) {
@@ -690,7 +762,7 @@ struct Plan : PlanBase {
   int estimate_rho(cudaStream_t s);
   // Make the Chebyshev parameters of this call available: explicit value, cached estimate, or a fresh estimate.
   int prepare_cheb(double rho_given, cudaStream_t s) {
-    if (rho_given > 0) {
+    if (rho_given > 0 && !use_two) {   // (the two-level methods also need the step length: they always estimate)
       cheb_rho = rho_given; rho_ps.assign(nsets, rho_given);
       if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * nsets));
       std::vector<T> h(nsets, (T)rho_given);
@@ -741,6 +813,7 @@ struct Plan : PlanBase {
     XEE_CHECK(cudaMemcpyAsync(x1, x0, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     if (prepare_maps(x0, x1, (const T*)f, d.nbatch)) return 1;
     if (mode == MODE_CHEBYSHEV && prepare_cheb(0.0, s)) return 1;   // before the start event: the spectral probe is not sweep time
+    cheb_rho_used = cheb_rho; cheb_gamma_used = use_two ? tl_gamma : 1.0;
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
     for (int cnt = 1; cnt <= nsw; ++cnt) {
@@ -818,15 +891,56 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   int rc = 0, parity = 0;   // current iterate lives in (parity ? e1 : e0)
   auto sweep = [&](int mode, int k) -> int {
     const T* src = parity ? e1 : e0; T* dst = parity ? e0 : e1;
-    SweepArgs<T> a = args(src, dst, zf, T(1), T(1), nullptr);
+    SweepArgs<T> a = args(src, dst, zf, (T)(use_two ? tl_gamma : 1.0), T(1), nullptr);
     a.nbatch = ns; a.rho_ps = rho_dev; a.cheb_k = k;
+    if (use_two) {   // one shared operator: the host-computed weight goes to the sweep kernel AND scales the coarse correction
+      a.rho_ps = nullptr;
+      a.omega = mode == MODE_CHEBYSHEV ? (T)cheb_omega_host(k, (double)rho_h[0]) : T(1);
+    }
     parity ^= 1;
     return launch_sweep(a, mode, false, s);
   };
+  if (use_two) {
+    // ---- two-level: the spectrum of M^-1 L (M^-1 = block lines + coarse space) is [lmin, lmax] with lmax possibly above 2,
+    // so the step length gamma is part of the method:  G = I - gamma M^-1 L,  gamma = 2 / (lmax + lmin),
+    // rho = (lmax - lmin) / (lmax + lmin).  lmax: power iteration on M^-1 L itself (with f = 0 one Jacobi sweep of step 1
+    // gives x - M^-1 L x; the difference is the next vector), from a vector that is smooth in r and alternates in z, like
+    // the dominant modes; 3 % safety.  lmin: the estimator below on G with the provisional step gamma0 = 1 / lmax, whose
+    // spectrum [0, 1 - lmin/lmax] is non-negative, so its dominant mode is the smooth one the probes look for.
+    for (int j = 1; j < d.ny - 1; ++j)
+      for (int i = 1; i < d.nx - 1; ++i) h[(size_t)j * d.nx + i] *= (T)((j & 1) ? -1.0 : 1.0) * (T)(1.0 + 0.25 * std::sin(0.7 * i + 1.3 * j));
+    XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+    tl_gamma = 1.0;
+    const int itL = env_int("XEE_LMAX_ITERS", 40);
+    for (int k = 1; k <= itL && !rc; ++k) {
+      const T* cur = parity ? e1 : e0;
+      if (k == itL) rc = rc || norms(cur, nA);
+      rc = rc || sweep(MODE_JACOBI, 1);                         // other = cur - M^-1 L cur   (parity now names `other`)
+      T* oth = parity ? e1 : e0; const T* was = parity ? e0 : e1;
+      tl::diff_kernel<T><<<256, 256, 0, s>>>(oth, was, nn);     // other = other - cur = -M^-1 L cur
+      XEE_LAUNCH_OK();
+      if (k == itL) rc = rc || norms(oth, nB);
+    }
+    if (rc) return 1;
+    tl_lmax = 1.03 * nB[0] / nA[0];
+    if (!(tl_lmax > 0.5 && tl_lmax < 8.0)) {
+      char msg[200]; snprintf(msg, sizeof msg, "xee: two-level: largest eigenvalue estimate of M^-1 L out of range (%.6e)", tl_lmax);
+      return fail(msg);
+    }
+    tl_gamma = 1.0 / tl_lmax;
+    // restore the smooth start vector of stage A
+    for (int j = 1; j < d.ny - 1; ++j)
+      for (int i = 1; i < d.nx - 1; ++i)
+        h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
+    XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+    parity = 0;
+  }
   // ---- stage A
   // probe lengths: the block-line splitting has a ~20x larger spectral gap than point Jacobi, so its modes separate in
   // proportionally fewer sweeps (64/64 measured: same sweep counts to tolerance as 200/200; 32/32 costs 2-3 % more sweeps)
-  const int itA = env_int("XEE_RHO_ITERS", use_line ? 64 : 200);
+  const int itA = env_int("XEE_RHO_ITERS", use_two ? 32 : use_line ? 64 : 200);
   for (int k = 1; k <= itA && !rc; ++k) {
     rc = sweep(MODE_JACOBI, 1);
     if (k == itA - 1) rc = rc || norms(parity ? e1 : e0, nA);
@@ -842,7 +956,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     }
   }
   // ---- stage B
-  const int rounds = env_int("XEE_RHO_ROUNDS", 4), p = env_int("XEE_RHO_PROBE", use_line ? 64 : 200);
+  const int rounds = env_int("XEE_RHO_ROUNDS", 4), p = env_int("XEE_RHO_PROBE", use_two ? 32 : use_line ? 64 : 200);
   std::vector<char> settled(ns, 0);
   auto lncosh = [](double x) { return x + std::log1p(std::exp(-2.0 * x)) - M_LN2; };
   for (int r = 0; r < rounds && !rc; ++r) {
@@ -876,6 +990,12 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     if (all_settled) break;
   }
   if (rc) return 1;
+  if (use_two) {   // rho[0] is the spectral radius of I - gamma0 M^-1 L: lmin = (1 - rho) / gamma0, then the final step and radius
+    tl_lmin = (1.0 - rho[0]) / tl_gamma;
+    tl_gamma = 2.0 / (tl_lmax + tl_lmin);
+    rho[0] = (tl_lmax - tl_lmin) / (tl_lmax + tl_lmin);
+    if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: two-level spectrum of M^-1 L: [%.4e, %.4f], gamma %.4f\n", tl_lmin, tl_lmax, tl_gamma);
+  }
   rho_ps = rho;
   for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];
   XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
@@ -956,6 +1076,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   const int mode = method_is_cheb() ? MODE_CHEBYSHEV : MODE_JACOBI;
   if (mode == MODE_CHEBYSHEV) {
     if (prepare_cheb(prm->rho_jacobi, s)) return 1;
+    cheb_rho_used = cheb_rho; cheb_gamma_used = use_two ? tl_gamma : 1.0;
   }
   init_state_kernel<T><<<(nb + 127) / 128, 128, 0, s>>>(st, nb, (T)prm->r1, (T)prm->r2, (const T*)prm->r1_per_solve);
   XEE_LAUNCH_OK();

@@ -75,7 +75,10 @@ template <class T> struct Cfg {
   static constexpr int FAC_BYTES = 2 * F_BYTES + 2 * A_BYTES;
   // result staging for the TMA store (two buffers, same [TH][FW] layout as the f box: odd chunk pitch, conflict-free STS.128)
   static constexpr int OUT_BYTES = F_BYTES, NOUT = 2;
+  // two-level method: per-thread restriction moments (S0, S1) of the residual, [2 buffers][TH rows][NSEG segments] double2
+  static constexpr int RES_BYTES = TH * NSEG * 16;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES + NOUT * OUT_BYTES;
+  static constexpr int SMEM_BYTES_TWO = SMEM_BYTES + 2 * RES_BYTES;
   static_assert((XW / V) % 2 == 1 && (FW / V) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
 // TMA store of one [1][TH][1][FW] box (4-D map: column-in-tile, tile column, row, solve) from shared memory; bulk async-group
@@ -266,9 +269,15 @@ struct LineArgs {
   double* partial;         // [n][ntiles] sum of r^2 (CHECK)
   int tiles_x, tiles_y, nchunks, chunk;
   int tstore;              // 1: results leave through shared memory + TMA stores (needs nx % TW == 0); 0: 128-bit global stores
+  T gamma;                 // Chebyshev: psi+ = omega ((psi - gamma z) - psi-) + psi-   (1 for the one-level methods)
+  double* cpart;           // TWO: [n][ntiles][32] restriction of the residual to the coarse grid, per tile (see xee_twolevel.cuh)
 };
 
-template <class T, bool CHEB, bool CHECK>
+// TWO = two-level method (xee_twolevel.cuh): the kernel also restricts the residual r = L psi - f of its tile to the coarse
+// grid (bilinear weights, nodes every 16 points in r and z; tiles are TH = 16 rows = one coarse cell high).  Every thread
+// forms the two moments S0 = sum r(e), S1 = sum e r(e) of its 8-point segment; one warp per (tile, solve), rotating, reduces
+// them over the 16 rows with the weights (1 - j/16) and j/16 and writes 32 doubles: [4 kinds][8 segments].
+template <class T, bool CHEB, bool CHECK, bool TWO = false>
 __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
     sweep_line_kernel(const __grid_constant__ LineArgs<T> a, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_xm, const __grid_constant__ CUtensorMap map_f,
@@ -334,6 +343,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
   const uint32_t auxa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + 2 * C::F_BYTES + r * C::AP + SEG * sg * 4);   // ... v, w (float)
   const uint32_t outa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + C::FAC_BYTES + r * C::FP + SEG * sg * C::ES);  // own cells of result buffer 0
   const bool tstore = a.tstore != 0;
+  const uint32_t resa = sm0 + (uint32_t)C::SMEM_BYTES;      // TWO: restriction moments (two buffers)
   uint32_t it = 0;
 
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -439,6 +449,14 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
         for (int e = 0; e < SEG; ++e)
           if ((inb >> e) & 1u) rr += (double)acc[e] * (double)acc[e];
       }
+      if (TWO) {   // restriction moments of the residual over the thread's interior points
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int e = 0; e < SEG; ++e)
+          if ((inb >> e) & 1u) { s0 += (double)acc[e]; s1 = fma((double)e, (double)acc[e], s1); }
+        const double mom[2] = {s0, s1};
+        sts16(resa + (it & 1u) * C::RES_BYTES + (uint32_t)((r * NSEG + sg) * 16), mom);
+      }
       // ---- Thomas solve of the segment: forward  y(i) = (r(i) - coe4(i) y(i-1)) m(i),  back  z(i) = y(i) - u(i) z(i+1)
       {
         T mf[SEG];
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
           load_seg<T>(sb + fofs + C::F_BYTES, xm);
           const T om = a.rho_ps ? (T)cheb_omega(a.cheb_k, (double)a.rho_ps[n]) : a.omega;
 #pragma unroll
-          for (int e = 0; e < SEG; ++e) out[e] = Rn<T>::fma(om, (x[e] - acc[e]) - xm[e], xm[e]);
+          for (int e = 0; e < SEG; ++e) out[e] = Rn<T>::fma(om, Rn<T>::fma(-a.gamma, acc[e], x[e]) - xm[e], xm[e]);
         }
       }
       if (tstore) {
@@ -507,6 +525,19 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
                        tile % a.tiles_x, j0, n);
           tma_store_commit();
         }
+      }
+      if (TWO && (uint32_t)(tid >> 5) == (it & 3u)) {
+        // this iteration's reducer warp: lane = kind * 8 + segment; kinds 0/1 = sum_j (1 - j/16) S0/S1 (coarse row of the
+        // tile's first row), kinds 2/3 = sum_j (j/16) S0/S1 (the next coarse row)
+        const int lane = tid & 31, kind = lane >> 3;
+        const double* red = reinterpret_cast<const double*>(smem_raw + C::SMEM_BYTES + (it & 1u) * C::RES_BYTES) + (lane & 7) * 2 + (kind & 1);
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+          const double wz = kind < 2 ? 1.0 - (double)j / TH : (double)j / TH;
+          t = fma(wz, red[j * NSEG * 2], t);
+        }
+        a.cpart[((size_t)n * ntiles + tile) * 32 + lane] = t;
       }
       if (!tstore) {
         T* const o = a.dst + ((size_t)n * nn + gofs);

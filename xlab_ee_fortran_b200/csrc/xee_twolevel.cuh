@@ -1,0 +1,212 @@
+// xee_twolevel.cuh — coarse-grid half of the TWO-LEVEL block-line methods (XEE_METHOD_LINE2_*), sm_100a.
+//
+// Same discrete problem, same residual r = L psi - f (do_elliptic's nine-term sum, xtt-lib-fortran/elliptic_tools.f90:77-85)
+// and the same stop rule (:193-233) as solve_elliptic.  The approximate inverse applied to the residual is ADDITIVE:
+//
+//     z = M^-1 r  +  P Ac^-1 P^T r,          psi' = psi - gamma z        (then Chebyshev acceleration)
+//
+// M = the 32-point radial block systems of xee_sweep_line.cuh, P = bilinear interpolation from a coarse grid with nodes
+// every HR = 16 radial and HZ = 16 vertical grid points (Dirichlet boundary: no nodes on it), Ac = P^T L P the Galerkin
+// coarse operator.  Why: the block-line Chebyshev iteration still needs ~950 sweeps at 512x256 because the modes that are
+// smooth in BOTH directions are damped slowly; the coarse space carries exactly those.  Measured with scipy on the bench
+// operator (scripts/prototypes/twolevel_spectrum.py): condition number of the preconditioned operator 3,877 -> 309,
+// Chebyshev sweeps to 1e-12 rms(f): 873-922 -> 251-255 (31 x 15 = 465 coarse unknowns).
+//
+// Per sweep: (1) sweep_line_kernel<.., TWO> relaxes the lines and leaves P^T r of its tile as 32 doubles per (tile, solve);
+// (2) coarse_gather_kernel sums the tile contributions per coarse node (fixed order: deterministic); (3) coarse_gemm_kernel
+// applies the dense inverse Ac^-1 to the whole batch, E[n] = Ac^-1 Rc[n] (465 x 465 x nbatch: one small fp64 GEMM), scaled by
+// -omega_k gamma; (4) prolong_add_kernel adds P E to the new iterate.  Once per operator: galerkin_kernel assembles Ac
+// (9-point coarse stencil) and gj_step_kernel inverts it (Gauss-Jordan without pivoting: Ac is definite like L).
+#pragma once
+#include "xee_kernels.cuh"
+
+namespace xee {
+namespace tl {
+
+constexpr int HR = 16, HZ = 16;   // coarse spacing in grid points (HR = 2 thread segments, HZ = the tile height of the v5 kernel)
+
+struct Dims {
+  int ncx, ncz, nc;   // coarse nodes at i = HR p (p = 1..ncx), j = HZ q (q = 1..ncz); node index = (q-1) ncx + (p-1)
+  int px, pz;         // the coarse correction is stored with a zero rim: [pz = ncz + 2][px = ncx + 2]
+  int ncp;            // nc padded to a multiple of 64 (GEMM tiles)
+};
+inline Dims dims(int nx, int ny) {
+  Dims d{};
+  d.ncx = (nx - 2) / HR; d.ncz = (ny - 2) / HZ; d.nc = d.ncx * d.ncz;
+  d.px = d.ncx + 2; d.pz = d.ncz + 2;
+  d.ncp = (d.nc + 63) / 64 * 64;
+  return d;
+}
+
+// 1-D hat function of node c (grid index) at grid index i; 0 outside the interior [1, n-2] (boundary points are not unknowns)
+__device__ __forceinline__ double hat(int i, int c, int h, int n) {
+  if (i < 1 || i > n - 2) return 0.0;
+  const int dd = i > c ? i - c : c - i;
+  return dd >= h ? 0.0 : 1.0 - (double)dd / (double)h;
+}
+
+// Ac = P^T L P, one block per coarse node q (column): L applied to the hat function of q on its support, tested against
+// the hats of the 9 neighbouring nodes.  Ac is [ncp][ncp] row-major, zero elsewhere, identity on the padding.
+template <class T>
+__global__ void __launch_bounds__(256) galerkin_kernel(const T* __restrict__ coe, double* __restrict__ Ac, int nx, int ny,
+                                                       int ncx, int ncz, int ncp) {
+  __shared__ double red[32];
+  const int q = blockIdx.x, qx = q % ncx + 1, qz = q / ncx + 1;
+  const int ic = HR * qx, jc = HZ * qz;
+  const size_t nn = (size_t)nx * ny;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  constexpr int W = 2 * HR + 1, H = 2 * HZ + 1;
+  for (int t = threadIdx.x; t < W * H; t += blockDim.x) {
+    const int i = ic - HR + t % W, j = jc - HZ + t / W;
+    if (i < 1 || i > nx - 2 || j < 1 || j > ny - 2) continue;
+    const size_t o = (size_t)j * nx + i;
+    // L phi_q at (i, j): slots 1..3 at j+1, 4..6 at j, 7..9 at j-1, each (i-1, i, i+1)
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int di = k % 3 - 1, dj = 1 - k / 3;
+      v += (double)coe[k * nn + o] * hat(i + di, ic, HR, nx) * hat(j + dj, jc, HZ, ny);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int a = k % 3 - 1, b = k / 3 - 1;
+      acc[k] += hat(i, ic + a * HR, HR, nx) * hat(j, jc + b * HZ, HZ, ny) * v;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const double tot = block_sum(acc[k], red, threadIdx.x, blockDim.x / 32);
+    const int px = qx + (k % 3 - 1), pz = qz + (k / 3 - 1);
+    if (threadIdx.x == 0 && px >= 1 && px <= ncx && pz >= 1 && pz <= ncz)
+      Ac[(size_t)((pz - 1) * ncx + (px - 1)) * ncp + q] = tot;
+  }
+}
+__global__ void pad_identity_kernel(double* __restrict__ A, int nc, int ncp) {
+  const int k = nc + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ncp) A[(size_t)k * ncp + k] = 1.0;
+}
+
+// One Gauss-Jordan step (pivot k) of the in-place inversion, out of place between two buffers so that a step is ONE launch:
+// row k is divided by the pivot, every other row i loses A[i][k] times it, column k becomes the multipliers.
+__global__ void gj_step_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int n, int ld, int k) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  const double piv = 1.0 / Ain[(size_t)k * ld + k];
+  const double rkj = j == k ? piv : Ain[(size_t)k * ld + j] * piv;
+  double out;
+  if (i == k) out = rkj;
+  else {
+    const double f = Ain[(size_t)i * ld + k];
+    out = (j == k ? 0.0 : Ain[(size_t)i * ld + j]) - f * rkj;
+  }
+  Aout[(size_t)i * ld + j] = out;
+}
+
+// Rc[n][node] = P^T r from the per-tile moments written by sweep_line_kernel<.., TWO>: part[n][tile][kind 0..3][segment 0..7],
+// kinds 0/1 = sum_j (1 - j/16) S0/S1 -> coarse row of the tile's first row, 2/3 = sum_j (j/16) S0/S1 -> the next coarse row.
+// A segment s (8 points from i = 8 s) lies in radial cell c = s / 2 at offset o0 = 8 (s & 1): its weight sum towards the cell's
+// right node is (o0 S0 + S1)/16, towards its left node S0 minus that.
+__global__ void coarse_gather_kernel(const double* __restrict__ part, double* __restrict__ Rc, const int* __restrict__ done,
+                                     int ntiles, int tiles_x, int tiles_y, int ncx, int ncz, int ncp) {
+  const int n = blockIdx.x;
+  if (done && done[n]) return;
+  const double* pn = part + (size_t)n * ntiles * 32;
+  const int nsegs = tiles_x * 8;
+  for (int idx = threadIdx.x; idx < ncx * ncz; idx += blockDim.x) {
+    const int p = idx % ncx + 1, q = idx / ncx + 1;
+    double tot = 0.0;
+#pragma unroll
+    for (int zc = 0; zc < 2; ++zc) {            // z-cell q-1 (kinds 2,3) then z-cell q (kinds 0,1)
+      const int ty = q - 1 + zc, kb = zc == 0 ? 2 : 0;
+      if (ty < 0 || ty >= tiles_y) continue;
+#pragma unroll
+      for (int ss = 0; ss < 4; ++ss) {          // segments 2p-2, 2p-1 (left cell), 2p, 2p+1 (right cell)
+        const int s = 2 * p - 2 + ss;
+        if (s < 0 || s >= nsegs) continue;
+        const double* t = pn + (size_t)(ty * tiles_x + s / 8) * 32 + (s & 7);
+        const double s0 = t[kb * 8], s1 = t[(kb + 1) * 8];
+        const double right = ((double)(8 * (s & 1)) * s0 + s1) * (1.0 / HR);
+        tot += ss < 2 ? right : s0 - right;
+      }
+    }
+    Rc[(size_t)n * ncp + idx] = tot;
+  }
+}
+
+// Cv[n] = scale * Ainv Rc[n] for the whole batch: C[n][i] = sum_j Ainv[i][j] Rc[n][j], 64 (i) x 32 (n) tile per block of 256
+// threads (4 x 2 per thread), K chunks of 16 through shared memory.  Ainv and Rc are padded to ncp (multiple of 64) with
+// zeros, so there is no edge handling in K or i.  Written into the rimmed layout Cv[n][pz][px] (interior only).
+constexpr int GM = 64, GN = 32, GK = 16;
+__global__ void __launch_bounds__(256) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
+                                                          double* __restrict__ Cv, const int* __restrict__ done, double scale,
+                                                          int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  __shared__ double As[GK][GM + 1], Bs[GK][GN + 1];
+  const int i0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  const int tid = threadIdx.x, ti = tid % 16, tn = tid / 16;     // thread: rows ti*4..+3 of i, cols tn*2..+1 of n
+  double c[4][2] = {};
+  for (int k0 = 0; k0 < ncp; k0 += GK) {
+    for (int t = tid; t < GM * GK; t += 256) { const int r = t / GK, k = t % GK; As[k][r] = Ainv[(size_t)(i0 + r) * ncp + k0 + k]; }
+    for (int t = tid; t < GN * GK; t += 256) {
+      const int r = t / GK, k = t % GK;
+      Bs[k][r] = n0 + r < nb ? Rc[(size_t)(n0 + r) * ncp + k0 + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) av[u] = As[k][ti * 4 + u];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) bv[v] = Bs[k][tn * 2 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) c[u][v] = fma(av[u], bv[v], c[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int n = n0 + tn * 2 + v;
+    if (n >= nb || (done && done[n])) continue;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + ti * 4 + u;
+      if (i < nc) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1)] = scale * c[u][v];
+    }
+  }
+}
+
+// x += P Cv on the interior points (bilinear; the rim of Cv is zero, which is the Dirichlet condition of the correction).
+// Thread = 2 consecutive radial points (16 bytes in fp64), block = 128 x 2 points... one row segment of 256 points.
+template <class T>
+__global__ void __launch_bounds__(128) prolong_add_kernel(T* __restrict__ x, const double* __restrict__ Cv, const int* __restrict__ done,
+                                                          int nx, int ny, int px, int pzpx) {
+  const int n = blockIdx.z, j = blockIdx.y;
+  if (j < 1 || j > ny - 2 || (done && done[n])) return;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= nx) return;
+  const double* cv = Cv + (size_t)n * pzpx;
+  const int q0 = j / HZ; const double tz = (double)(j % HZ) * (1.0 / HZ);
+  T* row = x + ((size_t)n * ny + j) * nx;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int ii = i + e;
+    if (ii < 1 || ii > nx - 2) continue;
+    const int p0 = ii / HR; const double tr = (double)(ii % HR) * (1.0 / HR);
+    const double c00 = cv[q0 * px + p0], c01 = cv[q0 * px + p0 + 1], c10 = cv[(q0 + 1) * px + p0], c11 = cv[(q0 + 1) * px + p0 + 1];
+    const double lo = fma(tr, c01 - c00, c00), hi = fma(tr, c11 - c10, c10);
+    row[ii] = (T)((double)row[ii] + fma(tz, hi - lo, lo));
+  }
+}
+
+// a <- a - b (power iteration on M^-1 L: with f = 0 one Jacobi sweep gives b = a - M^-1 L a)
+template <class T>
+__global__ void diff_kernel(T* __restrict__ a, const T* __restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = a[i] - b[i];
+}
+
+}  // namespace tl
+}  // namespace xee

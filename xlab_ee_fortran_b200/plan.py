@@ -14,8 +14,9 @@ from . import _lib
 
 F32, F64 = 0, 1
 ARITH_STRICT, ARITH_FAST = 0, 1
-JACOBI, CHEBYSHEV, LINE_JACOBI, LINE_CHEBYSHEV = 0, 1, 2, 3
-METHODS = {"jacobi": JACOBI, "chebyshev": CHEBYSHEV, "line_jacobi": LINE_JACOBI, "line_chebyshev": LINE_CHEBYSHEV}
+JACOBI, CHEBYSHEV, LINE_JACOBI, LINE_CHEBYSHEV, LINE2_JACOBI, LINE2_CHEBYSHEV = 0, 1, 2, 3, 4, 5
+METHODS = {"jacobi": JACOBI, "chebyshev": CHEBYSHEV, "line_jacobi": LINE_JACOBI, "line_chebyshev": LINE_CHEBYSHEV,
+           "line2_jacobi": LINE2_JACOBI, "line2_chebyshev": LINE2_CHEBYSHEV}
 
 
 class _PlanDesc(C.Structure):
@@ -171,6 +172,13 @@ class Plan:
         v = C.c_int(0); d = C.c_int(0); n = C.c_longlong(0)
         _lib.lib().xee_plan_kernel_info(self._h, C.byref(v), C.byref(d), C.byref(n))
         return v.value, d.value, n.value
+
+
+    def cheb_params(self):
+        """(rho, gamma) of the last accelerated call: spectral radius of I - gamma M^-1 L and the step length gamma."""
+        r = C.c_double(0); g = C.c_double(0)
+        _lib.lib().xee_plan_cheb_params(self._h, C.byref(r), C.byref(g))
+        return r.value, g.value
 
 
 def launch_count(reset=False) -> int:
