@@ -79,14 +79,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _lib = None
+_build_error = None
 
 
 def lib() -> C.CDLL:
     """The loaded C-ABI library.  Raises if it cannot be built/loaded: never a silent fallback."""
-    global _lib
+    global _lib, _build_error
+    if _build_error is not None:          # a failed build stays failed for this process: no minutes-long retry per call
+        raise _build_error
     if _lib is None:
         if not os.path.exists(SO):
-            build()
+            if os.environ.get("XEE_NO_BUILD"):
+                _build_error = RuntimeError(f"xee_b200: {SO} is missing and XEE_NO_BUILD is set")
+                raise _build_error
+            try:
+                build()
+            except Exception as e:
+                _build_error = e
+                raise
         _lib = C.CDLL(SO)
         _lib.xee_last_error.restype = C.c_char_p
         _lib.xee_build_info.restype = C.c_char_p

@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const T* __restrict__ coe
       Ac[(size_t)((pz - 1) * ncx + (px - 1)) * ncp + q] = tot;
   }
 }
-__global__ void pad_identity_kernel(double* __restrict__ A, int nc, int ncp) {
+static __global__ void pad_identity_kernel(double* __restrict__ A, int nc, int ncp) {
   const int k = nc + blockIdx.x * blockDim.x + threadIdx.x;
   if (k < ncp) A[(size_t)k * ncp + k] = 1.0;
 }
 
 // One Gauss-Jordan step (pivot k) of the in-place inversion, out of place between two buffers so that a step is ONE launch:
 // row k is divided by the pivot, every other row i loses A[i][k] times it, column k becomes the multipliers.
-__global__ void gj_step_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int n, int ld, int k) {
+static __global__ void gj_step_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int n, int ld, int k) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j >= n) return;
   const double piv = 1.0 / Ain[(size_t)k * ld + k];
@@ -108,7 +108,7 @@ __global__ void gj_step_kernel(const double* __restrict__ Ain, double* __restric
 // kinds 0/1 = sum_j (1 - j/16) S0/S1 -> coarse row of the tile's first row, 2/3 = sum_j (j/16) S0/S1 -> the next coarse row.
 // A segment s (8 points from i = 8 s) lies in radial cell c = s / 2 at offset o0 = 8 (s & 1): its weight sum towards the cell's
 // right node is (o0 S0 + S1)/16, towards its left node S0 minus that.
-__global__ void coarse_gather_kernel(const double* __restrict__ part, double* __restrict__ Rc, const int* __restrict__ done,
+static __global__ void coarse_gather_kernel(const double* __restrict__ part, double* __restrict__ Rc, const int* __restrict__ done,
                                      int ntiles, int tiles_x, int tiles_y, int ncx, int ncz, int ncp) {
   const int n = blockIdx.x;
   if (done && done[n]) return;
@@ -139,7 +139,7 @@ __global__ void coarse_gather_kernel(const double* __restrict__ part, double* __
 // threads (4 x 2 per thread), K chunks of 16 through shared memory.  Ainv and Rc are padded to ncp (multiple of 64) with
 // zeros, so there is no edge handling in K or i.  Written into the rimmed layout Cv[n][pz][px] (interior only).
 constexpr int GM = 64, GN = 32, GK = 16;
-__global__ void __launch_bounds__(256) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
+static __global__ void __launch_bounds__(256) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
                                                           double* __restrict__ Cv, const int* __restrict__ done, double scale,
                                                           int nb, int nc, int ncp, int ncx, int px, int pzpx) {
   __shared__ double As[GK][GM + 1], Bs[GK][GN + 1];
