@@ -137,6 +137,7 @@ struct SweepArgs {
   double* partial; // [n][ntiles] sum of r^2 per tile (check sweeps only)
   int ntiles;
   T* apply_out;    // APPLY mode: out = L psi
+  int two_slot;    // two-level methods: which coarse-correction slot (0/1) belongs to `src` (the other one to `dst`)
 };
 
 enum { MODE_JACOBI = 0, MODE_CHEBYSHEV = 1, MODE_APPLY = 2 };

@@ -193,7 +193,8 @@ struct Plan : PlanBase {
   tl::Dims tld{};
   double *tl_ainv = nullptr, *tl_tmp = nullptr;   // [ncp][ncp]: Ac^-1 (and the second Gauss-Jordan buffer)
   double *tl_part = nullptr;                      // [nbatch][ntiles][32] per-tile restriction of the residual
-  double *tl_rc = nullptr, *tl_cv = nullptr;      // [nbatch][ncp] restricted residual, [nbatch][pz][px] coarse correction
+  double *tl_rc = nullptr, *tl_cv = nullptr;      // [nbatch][ncp] restricted residual, [2 slots][nbatch][pz][px] coarse corrections
+  CUtensorMap map_cv{};                           //   ... and the TMA view of them ({px, pz, 2 nbatch}, boxes of 8 x 3)
   double tl_gamma = 1.0, tl_lmax = 0.0, tl_lmin = 0.0;
   bool tl_ready = false;
   // v4 (temporal blocking) sweep kernel: two more iterate buffers (passes cannot update in place), tiling, maps
@@ -300,15 +301,17 @@ struct Plan : PlanBase {
       if (use_two) {
         static_assert(ln::TH == tl::HZ && 2 * ln::SEG == tl::HR, "the two-level restriction assumes 16-row tiles and two 8-point segments per coarse cell");
         if (!d.shared_coe) return fail("xee: the two-level methods need a shared operator");
+        if (sizeof(T) != 8) return fail("xee: the two-level methods need fp64 fields");
         tld = tl::dims(d.nx, d.ny);
         if (tld.ncx < 1 || tld.ncz < 1) return fail("xee: the two-level methods need at least 18 x 18 grid points (one coarse node)");
         const size_t ab = sizeof(double) * (size_t)tld.ncp * tld.ncp;
         XEE_CHECK(pool_alloc(&tl_ainv, ab)); XEE_CHECK(pool_alloc(&tl_tmp, ab));
         XEE_CHECK(pool_alloc(&tl_part, sizeof(double) * (size_t)nb * nt * 32));
         XEE_CHECK(pool_alloc(&tl_rc, sizeof(double) * (size_t)nb * tld.ncp));
-        XEE_CHECK(pool_alloc(&tl_cv, sizeof(double) * (size_t)nb * tld.pz * tld.px));
+        XEE_CHECK(pool_alloc(&tl_cv, sizeof(double) * 2 * (size_t)nb * tld.pz * tld.px));
         XEE_CHECK(cudaMemsetAsync(tl_rc, 0, sizeof(double) * (size_t)nb * tld.ncp, own_stream));                 // padding stays 0
-        XEE_CHECK(cudaMemsetAsync(tl_cv, 0, sizeof(double) * (size_t)nb * tld.pz * tld.px, own_stream));         // rim stays 0
+        XEE_CHECK(cudaMemsetAsync(tl_cv, 0, sizeof(double) * 2 * (size_t)nb * tld.pz * tld.px, own_stream));     // rim stays 0
+        if (encode_map(&map_cv, tl_cv, tld.px, tld.pz, 2 * nb, 8, 3)) return 1;
       }
     } else if (want == 5) return fail("xee: kernel=5 is the line-relaxation kernel: select it with method = XEE_METHOD_LINE_*");
     // v4: temporal blocking.  auto: large shared-operator batches in FAST arithmetic (STRICT is bound by its true
@@ -507,17 +510,32 @@ struct Plan : PlanBase {
     return 0;
   }
   // Coarse half of one two-level sweep, after the sweep kernel has left P^T r per tile: gather, dense coarse solve for the
-  // batch (scaled by `scale` = -omega gamma), prolongation added to the new iterate.
-  int two_coarse(T* xnew, int nb, double scale, const int* done, cudaStream_t s) {
+  // batch, scaled by `scale` = -omega gamma, written as the coarse correction c of the NEW iterate (slot `slot`).  The fields
+  // are not touched: psi = y + P c is formed by whoever reads them (the next sweep; two_flush at the end).
+  double* two_cv(int slot, int nb) const { return tl_cv + (size_t)slot * nb * tld.pz * tld.px; }
+  int two_coarse(int slot, int nb, double scale, const int* done, cudaStream_t s) {
     const int nt = ln_tiles_x * ln_tiles_y;
     tl::coarse_gather_kernel<<<nb, 256, 0, s>>>(tl_part, tl_rc, done, nt, ln_tiles_x, ln_tiles_y, tld.ncx, tld.ncz, tld.ncp);
     XEE_LAUNCH_OK();
-    tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 256, 0, s>>>(tl_ainv, tl_rc, tl_cv, done, scale, nb, tld.nc, tld.ncp,
-                                                                                         tld.ncx, tld.px, tld.pz * tld.px);
-    XEE_LAUNCH_OK();
-    tl::prolong_add_kernel<T><<<dim3((d.nx + 255) / 256, d.ny, nb), 128, 0, s>>>(xnew, tl_cv, done, d.nx, d.ny, tld.px, tld.pz * tld.px);
+    tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 128, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc,
+                                                                                         tld.ncp, tld.ncx, tld.px, tld.pz * tld.px);
     XEE_LAUNCH_OK();
     return 0;
+  }
+  // c = 0 for both iterates: the stored fields ARE the iterates (start of a solve / of a probe)
+  int two_reset(int nb, cudaStream_t s) {
+    XEE_CHECK(cudaMemsetAsync(tl_cv, 0, sizeof(double) * 2 * (size_t)d.nbatch * tld.pz * tld.px, s));
+    (void)nb;
+    return 0;
+  }
+  // psi = y + P c made explicit in both buffers (b0 owns slot 0, b1 slot 1), then c = 0: the same state, stored plainly
+  int two_flush(T* b0, T* b1, int nb, cudaStream_t s) {
+    const dim3 g((((d.nx + 7) / 8) * d.ny + 255) / 256, 1, nb);
+    tl::prolong_add_kernel<T><<<g, 256, 0, s>>>(b0, two_cv(0, nb), nullptr, d.nx, d.ny, tld.px, tld.pz * tld.px);
+    XEE_LAUNCH_OK();
+    tl::prolong_add_kernel<T><<<g, 256, 0, s>>>(b1, two_cv(1, nb), nullptr, d.nx, d.ny, tld.px, tld.pz * tld.px);
+    XEE_LAUNCH_OK();
+    return two_reset(nb, s);
   }
   int coe_to_aos_host(void* coe_host) override {  // set 0 only (Fortran-facing cal_coe)
     T* tmp = nullptr;
@@ -600,7 +618,7 @@ struct Plan : PlanBase {
     constexpr int smem = TWO ? ln::Cfg<T>::SMEM_BYTES_TWO : ln::Cfg<T>::SMEM_BYTES;
     static std::atomic<unsigned long long> attr_done{0};
     if (opt_in_smem(sweep_line_kernel<T, CHEB, CHECK, TWO>, smem, attr_done)) return 1;
-    sweep_line_kernel<T, CHEB, CHECK, TWO><<<grid, ln::NT, smem, s>>>(A, mx, mxm, mf, mo);
+    sweep_line_kernel<T, CHEB, CHECK, TWO><<<grid, ln::NT, smem, s>>>(A, mx, mxm, mf, mo, TWO ? map_cv : mf);
     return 0;
   }
   template <bool CHEB, bool CHECK>
@@ -620,6 +638,10 @@ struct Plan : PlanBase {
     A.chunk = std::min(ln_chunk, a.nbatch); A.nchunks = (a.nbatch + A.chunk - 1) / A.chunk;
     A.tstore = ln_tstore ? 1 : 0;
     A.gamma = (T)(use_two ? tl_gamma : 1.0); A.cpart = tl_part;
+    // the coarse correction of `src` sits in slot a.two_slot, the one of the previous iterate (held by `dst`) in the other
+    // slot, which the coarse solve after this sweep overwrites with the correction of the NEW iterate; the batch index of a
+    // launch over a sub-batch (spectral probes) still strides by the plan's nbatch
+    A.cv_cur_z = a.two_slot * d.nbatch; A.cv_prev_z = (1 - a.two_slot) * d.nbatch;
     if (use_two && !tl_ready) return fail("xee: two-level method: the operator has not been set");
     const int grid = (int)std::min<long long>((long long)num_sms * ln::CTAS_PER_SM, (long long)ln_tiles_x * ln_tiles_y * A.nchunks);
     int rc;
@@ -629,7 +651,7 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     if (use_two) {   // psi' = psi - alpha (z + P E) (Jacobi) / y - omega gamma P E (Chebyshev; omega from the per-launch value)
       const double scale = mode == MODE_CHEBYSHEV ? -(double)a.omega * tl_gamma : -(double)a.alpha;
-      return two_coarse(a.dst, a.nbatch, scale, a.done, s);
+      return two_coarse(1 - a.two_slot, d.nbatch, scale, a.done, s);
     }
     return 0;
   }
@@ -816,15 +838,18 @@ struct Plan : PlanBase {
     cheb_rho_used = cheb_rho; cheb_gamma_used = use_two ? tl_gamma : 1.0;
     cudaEvent_t e0 = next_event(), e1 = next_event();
     XEE_CHECK(cudaEventRecord(e0, s));
+    if (use_two && two_reset(d.nbatch, s)) return 1;
     for (int cnt = 1; cnt <= nsw; ++cnt) {
       const T* src = (cnt & 1) ? x0 : x1;
       T* dst = (cnt & 1) ? x1 : x0;
       const double om = mode == MODE_CHEBYSHEV ? cheb_omega_host(cnt, cheb_rho) : 1.0;
       SweepArgs<T> a = args(src, dst, (const T*)f, (T)alpha, (T)om, nullptr);
+      a.two_slot = (cnt & 1) ? 0 : 1;      // x0 owns coarse slot 0, x1 slot 1
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, rms && cnt == nsw, s)) return 1;
     }
     sweep_launches += nsw; kernel_launches += nsw; variant_used = use_line ? 5 : use_tma ? 2 : 1; depth_used = 1;
+    if (use_two && two_flush(x0, x1, d.nbatch, s)) return 1;
     XEE_CHECK(cudaEventRecord(e1, s));
     if (nsw & 1) XEE_CHECK(cudaMemcpyAsync(x0, x1, sizeof(T) * nn * d.nbatch, cudaMemcpyDeviceToDevice, s));
     XEE_CHECK(cudaStreamSynchronize(s));
@@ -896,34 +921,43 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     if (use_two) {   // one shared operator: the host-computed weight goes to the sweep kernel AND scales the coarse correction
       a.rho_ps = nullptr;
       a.omega = mode == MODE_CHEBYSHEV ? (T)cheb_omega_host(k, (double)rho_h[0]) : T(1);
+      a.two_slot = parity;                  // e0 owns coarse slot 0, e1 slot 1
     }
     parity ^= 1;
     return launch_sweep(a, mode, false, s);
   };
+  // two-level: the probe vectors are (stored field, coarse vector) pairs; norms and differences need them made explicit
+  auto flush = [&]() -> int { return use_two ? two_flush(e0, e1, ns, s) : 0; };
+  if (use_two && two_reset(ns, s)) return 1;
   if (use_two) {
-    // ---- two-level: the spectrum of M^-1 L (M^-1 = block lines + coarse space) is [lmin, lmax] with lmax possibly above 2,
-    // so the step length gamma is part of the method:  G = I - gamma M^-1 L,  gamma = 2 / (lmax + lmin),
-    // rho = (lmax - lmin) / (lmax + lmin).  lmax: power iteration on M^-1 L itself (with f = 0 one Jacobi sweep of step 1
-    // gives x - M^-1 L x; the difference is the next vector), from a vector that is smooth in r and alternates in z, like
-    // the dominant modes; 3 % safety.  lmin: the estimator below on G with the provisional step gamma0 = 1 / lmax, whose
-    // spectrum [0, 1 - lmin/lmax] is non-negative, so its dominant mode is the smooth one the probes look for.
+    // ---- two-level: the spectrum of M^-1 L (M^-1 = block lines + coarse space) is [lmin, lmax] with lmax around 2, possibly
+    // above it, so the step length gamma is part of the method:  G = I - gamma M^-1 L,  gamma = 2 / (lmax + lmin),
+    // rho = (lmax - lmin) / (lmax + lmin).
+    // lmax: the block-line part alone is bounded by 2 (L and its block-diagonal part are diagonally dominant with the same
+    // sign), but the modes just below 2 (oscillating in z) form a dense cluster in which a power iteration creeps (measured:
+    // 1.90 after 40 and 1.98 after 160 iterations for a true 1.9986), and UNDER-estimating lmax makes the Chebyshev iteration
+    // diverge.  So: lmax = 1.02 max(2, power-iteration estimate): the iteration is only there to catch a coarse space that
+    // pushes an isolated eigenvalue above 2 (such a mode separates quickly).  Over-estimating lmax by 2 % costs 1 % in sweeps.
+    // lmin: the estimator below on G with the provisional step gamma0 = 1 / lmax, whose spectrum [0, 1 - lmin/lmax] is
+    // non-negative, so its dominant mode is the smooth one the probes look for.
     for (int j = 1; j < d.ny - 1; ++j)
       for (int i = 1; i < d.nx - 1; ++i) h[(size_t)j * d.nx + i] *= (T)((j & 1) ? -1.0 : 1.0) * (T)(1.0 + 0.25 * std::sin(0.7 * i + 1.3 * j));
     XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
     XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
     tl_gamma = 1.0;
-    const int itL = env_int("XEE_LMAX_ITERS", 40);
+    const int itL = env_int("XEE_LMAX_ITERS", 60);
     for (int k = 1; k <= itL && !rc; ++k) {
       const T* cur = parity ? e1 : e0;
       if (k == itL) rc = rc || norms(cur, nA);
       rc = rc || sweep(MODE_JACOBI, 1);                         // other = cur - M^-1 L cur   (parity now names `other`)
+      rc = rc || flush();
       T* oth = parity ? e1 : e0; const T* was = parity ? e0 : e1;
       tl::diff_kernel<T><<<256, 256, 0, s>>>(oth, was, nn);     // other = other - cur = -M^-1 L cur
       XEE_LAUNCH_OK();
       if (k == itL) rc = rc || norms(oth, nB);
     }
     if (rc) return 1;
-    tl_lmax = 1.03 * nB[0] / nA[0];
+    tl_lmax = 1.02 * std::max(2.0, 1.01 * nB[0] / nA[0]);
     if (!(tl_lmax > 0.5 && tl_lmax < 8.0)) {
       char msg[200]; snprintf(msg, sizeof msg, "xee: two-level: largest eigenvalue estimate of M^-1 L out of range (%.6e)", tl_lmax);
       return fail(msg);
@@ -943,6 +977,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   const int itA = env_int("XEE_RHO_ITERS", use_two ? 32 : use_line ? 64 : 200);
   for (int k = 1; k <= itA && !rc; ++k) {
     rc = sweep(MODE_JACOBI, 1);
+    if (k >= itA - 1) rc = rc || flush();
     if (k == itA - 1) rc = rc || norms(parity ? e1 : e0, nA);
     if (k == itA) rc = rc || norms(parity ? e1 : e0, nB);
   }
@@ -966,6 +1001,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     XEE_CHECK(cudaMemcpyAsync(parity ? e0 : e1, parity ? e1 : e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
     for (int k = 1; k <= 2 * p && !rc; ++k) {
       rc = sweep(MODE_CHEBYSHEV, k);
+      if (k == p || k == 2 * p) rc = rc || flush();
       if (k == p) rc = rc || norms(parity ? e1 : e0, nA);
       if (k == 2 * p) rc = rc || norms(parity ? e1 : e0, nB);
     }
@@ -1127,6 +1163,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     XEE_CHECK(cudaMemcpyAsync(x1, x0, fbytes, cudaMemcpyDeviceToDevice, s));
     if (prepare_maps(x0, x1, fd, nb)) return 1;
   }
+  if (use_two && two_reset(nb, s)) return 1;
   int tb_pass = 0;
   variant_used = use_line ? 5 : use_tb ? 4 : use_tma ? 2 : 1; depth_used = use_tb ? tb_depth : 1;
   const int ninterior = (d.nx - 2) * (d.ny - 2);
@@ -1153,6 +1190,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
       const bool check = (cnt % check_step) == 0;                                // :179-183
       const double om = mode == MODE_CHEBYSHEV ? cheb_omega_host(cnt, cheb_rho) : 1.0;
       SweepArgs<T> a = args(src, dst, fd, (T)prm->alpha, (T)om, st.done);
+      a.two_slot = (cnt & 1) ? 0 : 1;      // x0 owns coarse slot 0, x1 slot 1
       if (mode == MODE_CHEBYSHEV && !d.shared_coe) { a.rho_ps = rho_dev; a.cheb_k = cnt; }
       if (launch_sweep(a, mode, check, s)) return 1;
     }
@@ -1160,8 +1198,9 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     if (!use_tb) kernel_launches += chunk;
     XEE_CHECK(cudaEventRecord(e1, s));
     if ((cnt % check_step) == 0) {
+      // an accelerated iteration with a wrong spectral estimate diverges: a non-finite residual always stops it (err bit 1)
       finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, use_tb ? tb_ntiles() : sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
-                                                  lost_rate, max_iter, prm->detect_explode, prm->stall_checks);
+                                                  lost_rate, max_iter, prm->detect_explode || mode == MODE_CHEBYSHEV, prm->stall_checks);
       XEE_LAUNCH_OK();
       const int slot = check_idx & 3;
       XEE_CHECK(cudaMemcpyAsync(&h_active[slot], st.active, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1191,6 +1230,7 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     finalize_maxiter_kernel<T><<<(nb + 127) / 128, 128, 0, s>>>(st, nb, max_iter);
     XEE_LAUNCH_OK();
   }
+  if (use_two && two_flush(x0, x1, nb, s)) return 1;    // psi = y + P c in both buffers (final and penultimate iterate of every solve)
   dim3 g((unsigned)std::min<size_t>((nn + 255) / 256, 64), nb);
   if (use_tb) select_result_tb_kernel<T><<<g, 256, 0, s>>>(x0, x1, x2, x3, st.iters, (long long)nn, check_step, tb_depth);
   else select_result_kernel<T><<<g, 256, 0, s>>>(x0, x1, st.iters, (long long)nn, 1);

@@ -78,7 +78,9 @@ template <class T> struct Cfg {
   // two-level method: per-thread restriction moments (S0, S1) of the residual, [2 buffers][TH rows][NSEG segments] double2
   static constexpr int RES_BYTES = TH * NSEG * 16;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + FAC_BYTES + NOUT * OUT_BYTES;
-  static constexpr int SMEM_BYTES_TWO = SMEM_BYTES + 2 * RES_BYTES;
+  // two-level method: every stage also carries two 3 x 8 patches of coarse-correction values (current / previous iterate)
+  static constexpr int CP_RAW = 3 * 8 * 8, CP_BYTES = 2 * 256;
+  static constexpr int SMEM_BYTES_TWO = SMEM_BYTES + NSTAGE * CP_BYTES + 2 * RES_BYTES;
   static_assert((XW / V) % 2 == 1 && (FW / V) % 2 == 1, "row pitches must be an odd number of 16-byte chunks");
 };
 // TMA store of one [1][TH][1][FW] box (4-D map: column-in-tile, tile column, row, solve) from shared memory; bulk async-group
@@ -271,9 +273,14 @@ struct LineArgs {
   int tstore;              // 1: results leave through shared memory + TMA stores (needs nx % TW == 0); 0: 128-bit global stores
   T gamma;                 // Chebyshev: psi+ = omega ((psi - gamma z) - psi-) + psi-   (1 for the one-level methods)
   double* cpart;           // TWO: [n][ntiles][32] restriction of the residual to the coarse grid, per tile (see xee_twolevel.cuh)
+  int cv_cur_z, cv_prev_z; // TWO: first index (slot * nbatch) of the coarse corrections of the iterate read / of the previous one in map_cv
 };
 
-// TWO = two-level method (xee_twolevel.cuh): the kernel also restricts the residual r = L psi - f of its tile to the coarse
+// TWO = two-level method (xee_twolevel.cuh).  The iterates live in global memory WITHOUT their latest coarse-grid correction:
+// the field y_k is stored, the iterate is psi_k = y_k + P c_k with c_k a small coarse vector per solve (written by the coarse
+// solve that follows every sweep).  The kernel adds P c_k on the fly to everything it reads (psi tile with halo: bilinear,
+// linear along the thread's 8 points; likewise P c_{k-1} to psi_{k-1}) - a 3 x 8 patch of coarse values per iterate travels
+// with the TMA stage - so the coarse correction costs no pass over the fields.  The kernel also restricts the residual r = L psi - f of its tile to the coarse
 // grid (bilinear weights, nodes every 16 points in r and z; tiles are TH = 16 rows = one coarse cell high).  Every thread
 // forms the two moments S0 = sum r(e), S1 = sum e r(e) of its 8-point segment; one warp per (tile, solve), rotating, reduces
 // them over the 16 rows with the weights (1 - j/16) and j/16 and writes 32 doubles: [4 kinds][8 segments].
@@ -281,11 +288,14 @@ template <class T, bool CHEB, bool CHECK, bool TWO = false>
 __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
     sweep_line_kernel(const __grid_constant__ LineArgs<T> a, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_xm, const __grid_constant__ CUtensorMap map_f,
-                      const __grid_constant__ CUtensorMap map_out) {
+                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_cv) {
   using namespace ln;
   using tma::mbar_init; using tma::mbar_expect_tx; using tma::mbar_wait; using tma::tma_load_3d;
   using C = Cfg<T>;
   constexpr int V = C::V, NV = C::NV;
+  constexpr int SB = C::STAGE_BYTES + (TWO ? C::CP_BYTES : 0);     // stage stride
+  constexpr int AFTER = NSTAGE * SB;                                // factor cells, result staging, restriction moments follow
+  constexpr int RES_OFS = AFTER + C::FAC_BYTES + C::NOUT * C::OUT_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NSTAGE];
   __shared__ double red[NT / 32];
@@ -321,8 +331,12 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
       const int tile = pu % ntiles;
       const int i0 = (tile % a.tiles_x) * TW, j0 = (tile / a.tiles_x) * TH;
       const int s = issued % NSTAGE;
-      unsigned char* st = smem_raw + (size_t)s * C::STAGE_BYTES;
-      mbar_expect_tx(&full_bar[s], (uint32_t)(C::X_RAW + (CHEB ? 2 : 1) * C::F_RAW));
+      unsigned char* st = smem_raw + (size_t)s * SB;
+      mbar_expect_tx(&full_bar[s], (uint32_t)(C::X_RAW + (CHEB ? 2 : 1) * C::F_RAW + (TWO ? (CHEB ? 2 : 1) * C::CP_RAW : 0)));
+      if (TWO) {   // coarse patches: nodes 4 tx - 1 .. 4 tx + 6 (node p sits in column p + 1), coarse rows ty - 1 .. ty + 1
+        tma_load_3d(st + C::STAGE_BYTES, &map_cv, 4 * (tile % a.tiles_x), tile / a.tiles_x - 1, a.cv_cur_z + pn, &full_bar[s]);
+        if (CHEB) tma_load_3d(st + C::STAGE_BYTES + 256, &map_cv, 4 * (tile % a.tiles_x), tile / a.tiles_x - 1, a.cv_prev_z + pn, &full_bar[s]);
+      }
       tma_load_3d(st, &map_x, i0 - V, j0 - 1, pn, &full_bar[s]);
       tma_load_3d(st + C::X_BYTES, &map_f, i0, j0, pn, &full_bar[s]);
       if (CHEB) tma_load_3d(st + C::X_BYTES + C::F_BYTES, &map_xm, i0, j0, pn, &full_bar[s]);
@@ -339,11 +353,11 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
   const uint32_t sm0 = tma::smem_u32(smem_raw);
   const uint32_t xofs = (uint32_t)((r + 1) * C::XP + (V + SEG * sg) * C::ES);   // own segment in the psi box
   const uint32_t fofs = (uint32_t)(C::X_BYTES + r * C::FP + SEG * sg * C::ES);  // ... in the f box
-  const uint32_t faca = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + r * C::FP + SEG * sg * C::ES);   // own cells of the factor planes m, u
-  const uint32_t auxa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + 2 * C::F_BYTES + r * C::AP + SEG * sg * 4);   // ... v, w (float)
-  const uint32_t outa = sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + C::FAC_BYTES + r * C::FP + SEG * sg * C::ES);  // own cells of result buffer 0
+  const uint32_t faca = sm0 + (uint32_t)(AFTER + r * C::FP + SEG * sg * C::ES);   // own cells of the factor planes m, u
+  const uint32_t auxa = sm0 + (uint32_t)(AFTER + 2 * C::F_BYTES + r * C::AP + SEG * sg * 4);   // ... v, w (float)
+  const uint32_t outa = sm0 + (uint32_t)(AFTER + C::FAC_BYTES + r * C::FP + SEG * sg * C::ES);  // own cells of result buffer 0
   const bool tstore = a.tstore != 0;
-  const uint32_t resa = sm0 + (uint32_t)C::SMEM_BYTES;      // TWO: restriction moments (two buffers)
+  const uint32_t resa = sm0 + (uint32_t)RES_OFS;            // TWO: restriction moments (two buffers)
   uint32_t it = 0;
 
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -358,6 +372,18 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
 #pragma unroll
     for (int e = 0; e < SEG; ++e)
       if (gi + e >= 1 && gi + e < a.nx - 1 && gj >= 1 && gj < a.ny - 1) inb |= 1u << e;
+    // TWO: where the coarse correction applies.  It vanishes by itself on the bottom row and the first column (zero rim of
+    // the coarse values); on the top row (j = ny-1) and the last column (i = nx-1) it must be switched off: Dirichlet values.
+    // cmask bit k: column gi - 1 + k (k = 0..9: left neighbour, the 8 points, right neighbour) is not the last column.
+    unsigned cmask = 0x3ffu;
+    double fu = 1.0, fm = 1.0;      // row factors of the stencil rows j+1 and j
+    if (TWO) {
+#pragma unroll
+      for (int k = 0; k < SEG + 2; ++k)
+        if (gi - 1 + k >= a.nx - 1) cmask &= ~(1u << k);
+      if (gj + 1 >= a.ny - 1) fu = 0.0;
+      if (gj >= a.ny - 1) fm = 0.0;
+    }
     // stop flags of this unit's solves (chunk <= 32) as one register mask: no shared-memory load per (tile, solve)
     uint32_t umask = 0;
     if (a.done != nullptr) {
@@ -409,13 +435,41 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
       if ((umask >> (n - n0)) & 1u) continue;
       const uint32_t s = it % NSTAGE;
       mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
-      const uint32_t sb = sm0 + s * C::STAGE_BYTES;
+      const uint32_t sb = sm0 + s * SB;
       const uint32_t xa = sb + xofs;
       // ---- residual: the nine-term sum in the reference's order (rows j+1, j, j-1; i-1, i, i+1), minus f
       T acc[SEG];
+      // TWO: coarse values of this thread's cell: patch columns cl, cl+1, cl+2 = nodes p-1, p, p+1 (p = left node of the cell
+      // of the segment), patch rows 0..2 = coarse rows ty-1, ty, ty+1.  Along z the correction is linear in the local row
+      // offset zo in [0, 16]; the halo row zo = -1 lies in the cell below.
+      const double* pc = reinterpret_cast<const double*>(smem_raw + (size_t)s * SB + C::STAGE_BYTES) + (sg >> 1);
+      auto add_corr = [&](T (&w)[SEG + 2], const double* pq, int zo, double rowf) {
+        // node values of the row: V_m = c1_m + slope_m zo, slope towards the upper coarse row (zo >= 0) or the lower one (zo = -1)
+        double vv[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const double c1 = pq[8 + m];
+          const double sl = zo >= 0 ? (pq[16 + m] - c1) : (c1 - pq[m]);
+          vv[m] = fma(sl, (double)zo * (1.0 / 16.0), c1) * rowf;
+        }
+        const double S = (vv[2] - vv[1]) * (1.0 / 16.0);
+        const double b0 = fma(S, (double)(SEG * (sg & 1)), vv[1]);              // value at the segment's first point
+        const double left = (sg & 1) ? b0 - S : fma(vv[1] - vv[0], 15.0 / 16.0, vv[0]);   // point before it: same cell / the cell to the left
+        if (cmask == 0x3ffu) {
+          w[0] += (T)left;
+#pragma unroll
+          for (int k = 1; k < SEG + 2; ++k) w[k] += (T)fma(S, (double)(k - 1), b0);
+        } else {
+          if (cmask & 1u) w[0] += (T)left;
+#pragma unroll
+          for (int k = 1; k < SEG + 2; ++k)
+            if ((cmask >> k) & 1u) w[k] += (T)fma(S, (double)(k - 1), b0);
+        }
+      };
       {
         T w[SEG + 2];
         load_row<T>(xa + C::XP, w);
+        if (TWO) add_corr(w, pc, r + 1, fu);
 #pragma unroll
         for (int e = 0; e < SEG; ++e) acc[e] = cf[0][e] * w[e];
 #pragma unroll
@@ -423,6 +477,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
 #pragma unroll
         for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(cf[2][e], w[e + 2], acc[e]);
         load_row<T>(xa, w);
+        if (TWO) add_corr(w, pc, r, fm);
 #pragma unroll
         for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(cf[3][e], w[e], acc[e]);
 #pragma unroll
@@ -430,6 +485,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
 #pragma unroll
         for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(cf[5][e], w[e + 2], acc[e]);
         load_row<T>(xa - C::XP, w);
+        if (TWO) add_corr(w, pc, r - 1, 1.0);
 #pragma unroll
         for (int e = 0; e < SEG; ++e) acc[e] = Rn<T>::fma(cf[6][e], w[e], acc[e]);
 #pragma unroll
@@ -493,14 +549,25 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
       // ---- update
       T out[SEG];
       {
+        // TWO: the coarse correction at the thread's own points (interior points only), for the current and the previous iterate
+        auto own_corr = [&](T (&v)[SEG], const double* pq) {
+          const double tz = (double)r * (1.0 / 16.0);
+          const double vl = fma(pq[17] - pq[9], tz, pq[9]), vr = fma(pq[18] - pq[10], tz, pq[10]);
+          const double S = (vr - vl) * (1.0 / 16.0), b0 = fma(S, (double)(SEG * (sg & 1)), vl);
+#pragma unroll
+          for (int e = 0; e < SEG; ++e)
+            if ((inb >> e) & 1u) v[e] += (T)fma(S, (double)e, b0);
+        };
         T x[SEG];
         load_seg<T>(xa, x);
+        if (TWO) own_corr(x, pc);
         if (!CHEB) {
 #pragma unroll
           for (int e = 0; e < SEG; ++e) out[e] = Rn<T>::fma(-a.alpha, acc[e], x[e]);
         } else {
           T xm[SEG];
           load_seg<T>(sb + fofs + C::F_BYTES, xm);
+          if (TWO) own_corr(xm, pc + 32);
           const T om = a.rho_ps ? (T)cheb_omega(a.cheb_k, (double)a.rho_ps[n]) : a.omega;
 #pragma unroll
           for (int e = 0; e < SEG; ++e) out[e] = Rn<T>::fma(om, Rn<T>::fma(-a.gamma, acc[e], x[e]) - xm[e], xm[e]);
@@ -521,7 +588,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
         if (tstore) {
           // box [TH][FW] at (column 0 of tile column tile % tiles_x, row j0, solve n): columns >= TW and rows >= ny are out
           // of bounds of the 4-D map and are not written
-          tma_store_4d(&map_out, sm0 + (uint32_t)(NSTAGE * C::STAGE_BYTES + C::FAC_BYTES) + (it & 1u) * C::OUT_BYTES, 0,
+          tma_store_4d(&map_out, sm0 + (uint32_t)(AFTER + C::FAC_BYTES) + (it & 1u) * C::OUT_BYTES, 0,
                        tile % a.tiles_x, j0, n);
           tma_store_commit();
         }
@@ -530,13 +597,14 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
         // this iteration's reducer warp: lane = kind * 8 + segment; kinds 0/1 = sum_j (1 - j/16) S0/S1 (coarse row of the
         // tile's first row), kinds 2/3 = sum_j (j/16) S0/S1 (the next coarse row)
         const int lane = tid & 31, kind = lane >> 3;
-        const double* red = reinterpret_cast<const double*>(smem_raw + C::SMEM_BYTES + (it & 1u) * C::RES_BYTES) + (lane & 7) * 2 + (kind & 1);
-        double t = 0.0;
+        const double* red = reinterpret_cast<const double*>(smem_raw + RES_OFS + (it & 1u) * C::RES_BYTES) + (lane & 7) * 2 + (kind & 1);
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};       // four short chains instead of one of 16
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           const double wz = kind < 2 ? 1.0 - (double)j / TH : (double)j / TH;
-          t = fma(wz, red[j * NSEG * 2], t);
+          t4[j & 3] = fma(wz, red[j * NSEG * 2], t4[j & 3]);
         }
+        const double t = (t4[0] + t4[1]) + (t4[2] + t4[3]);
         a.cpart[((size_t)n * ntiles + tile) * 32 + lane] = t;
       }
       if (!tstore) {

@@ -14,9 +14,11 @@
 //
 // Per sweep: (1) sweep_line_kernel<.., TWO> relaxes the lines and leaves P^T r of its tile as 32 doubles per (tile, solve);
 // (2) coarse_gather_kernel sums the tile contributions per coarse node (fixed order: deterministic); (3) coarse_gemm_kernel
-// applies the dense inverse Ac^-1 to the whole batch, E[n] = Ac^-1 Rc[n] (465 x 465 x nbatch: one small fp64 GEMM), scaled by
-// -omega_k gamma; (4) prolong_add_kernel adds P E to the new iterate.  Once per operator: galerkin_kernel assembles Ac
-// (9-point coarse stencil) and gj_step_kernel inverts it (Gauss-Jordan without pivoting: Ac is definite like L).
+// applies the dense inverse Ac^-1 to the whole batch, E[n] = Ac^-1 Rc[n] (465 x 465 x nbatch: one small fp64 GEMM on the FP64
+// tensor cores), scaled by -omega_k gamma.  The prolongation P E is NOT a pass over the fields: the iterate is kept as
+// (stored field y, coarse vector c), psi = y + P c, and the sweep kernel adds P c to what it reads (xee_sweep_line.cuh);
+// prolong_add_kernel applies it once, when a solve ends.  Once per operator: galerkin_kernel assembles Ac (9-point coarse
+// stencil) and gj_step_kernel inverts it (Gauss-Jordan without pivoting: Ac is definite like L).
 #pragma once
 #include "xee_kernels.cuh"
 
@@ -27,13 +29,16 @@ constexpr int HR = 16, HZ = 16;   // coarse spacing in grid points (HR = 2 threa
 
 struct Dims {
   int ncx, ncz, nc;   // coarse nodes at i = HR p (p = 1..ncx), j = HZ q (q = 1..ncz); node index = (q-1) ncx + (p-1)
-  int px, pz;         // the coarse correction is stored with a zero rim: [pz = ncz + 2][px = ncx + 2]
+  int px, pz;         // the coarse correction is stored with a zero rim, node (p, q) at [q][p + 1]: pz = ncz + 2 rows of pitch
+                      // px = ncx + 3 rounded up to even (one spare column in front, so that the TMA boxes of the sweep kernel,
+                      // which start at node 4 tx - 1, begin on a 16-byte boundary)
   int ncp;            // nc padded to a multiple of 64 (GEMM tiles)
 };
+constexpr int COL0 = 1;   // column of node 0
 inline Dims dims(int nx, int ny) {
   Dims d{};
   d.ncx = (nx - 2) / HR; d.ncz = (ny - 2) / HZ; d.nc = d.ncx * d.ncz;
-  d.px = d.ncx + 2; d.pz = d.ncz + 2;
+  d.px = (d.ncx + 3 + 1) & ~1; d.pz = d.ncz + 2;
   d.ncp = (d.nc + 63) / 64 * 64;
   return d;
 }
@@ -135,70 +140,87 @@ static __global__ void coarse_gather_kernel(const double* __restrict__ part, dou
   }
 }
 
-// Cv[n] = scale * Ainv Rc[n] for the whole batch: C[n][i] = sum_j Ainv[i][j] Rc[n][j], 64 (i) x 32 (n) tile per block of 256
-// threads (4 x 2 per thread), K chunks of 16 through shared memory.  Ainv and Rc are padded to ncp (multiple of 64) with
-// zeros, so there is no edge handling in K or i.  Written into the rimmed layout Cv[n][pz][px] (interior only).
-constexpr int GM = 64, GN = 32, GK = 16;
-static __global__ void __launch_bounds__(256) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
-                                                          double* __restrict__ Cv, const int* __restrict__ done, double scale,
-                                                          int nb, int nc, int ncp, int ncx, int px, int pzpx) {
-  __shared__ double As[GK][GM + 1], Bs[GK][GN + 1];
-  const int i0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
-  const int tid = threadIdx.x, ti = tid % 16, tn = tid / 16;     // thread: rows ti*4..+3 of i, cols tn*2..+1 of n
-  double c[4][2] = {};
-  for (int k0 = 0; k0 < ncp; k0 += GK) {
-    for (int t = tid; t < GM * GK; t += 256) { const int r = t / GK, k = t % GK; As[k][r] = Ainv[(size_t)(i0 + r) * ncp + k0 + k]; }
-    for (int t = tid; t < GN * GK; t += 256) {
-      const int r = t / GK, k = t % GK;
-      Bs[k][r] = n0 + r < nb ? Rc[(size_t)(n0 + r) * ncp + k0 + k] : 0.0;
-    }
-    __syncthreads();
+// Cv[n] = scale * Ainv Rc[n] for the whole batch: C[i][n] = sum_k Ainv[i][k] Rc[n][k], one small fp64 GEMM (ncp x nbatch x ncp)
+// on the FP64 tensor cores (mma.sync m8n8k4: DMMA).  Both operands are k-contiguous in memory, which is exactly the
+// row-major A / column-major B fragment layout of the instruction (thread (g = lane/4, t = lane%4) holds A[g][t] and
+// B[t][g]), so the fragments are loaded straight from global memory (2 MB + 2 MB, L2-resident, re-use through L1) with no
+// shared-memory staging.  Warp tile 32 (i) x 16 (n) = 4 x 2 accumulator fragments, block = 4 warps = 64 x 32.  Ainv and Rc
+// are padded to ncp (multiple of 64) with zeros: no edge handling in k or i; rows n >= nbatch are clamped and discarded.
+// Written into the rimmed layout Cv[n][pz][px] (interior only).
+constexpr int GM = 64, GN = 32;
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
+                                                                 double* __restrict__ Cv, const int* __restrict__ done, double scale,
+                                                                 int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = blockIdx.x * GM + (warp & 1) * 32, n0 = blockIdx.y * GN + (warp >> 1) * 16;
+  double c[4][2][2] = {};
+  const double* ap[4]; const double* bp[2];
 #pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      double av[4], bv[2];
+  for (int x = 0; x < 4; ++x) ap[x] = Ainv + (size_t)(i0 + 8 * x + g) * ncp + t;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) av[u] = As[k][ti * 4 + u];
+  for (int y = 0; y < 2; ++y) bp[y] = Rc + (size_t)min(n0 + 8 * y + g, nb - 1) * ncp + t;
+#pragma unroll 8
+  for (int k0 = 0; k0 < ncp; k0 += 4) {
+    double a[4], b[2];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) bv[v] = Bs[k][tn * 2 + v];
+    for (int x = 0; x < 4; ++x) a[x] = __ldg(ap[x] + k0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int y = 0; y < 2; ++y) b[y] = __ldg(bp[y] + k0);
 #pragma unroll
-        for (int v = 0; v < 2; ++v) c[u][v] = fma(av[u], bv[v], c[u][v]);
-    }
-    __syncthreads();
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) dmma_m8n8k4(c[x][y], a[x], b[y]);
   }
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
-    const int n = n0 + tn * 2 + v;
-    if (n >= nb || (done && done[n])) continue;
+  for (int y = 0; y < 2; ++y)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + ti * 4 + u;
-      if (i < nc) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1)] = scale * c[u][v];
+    for (int v = 0; v < 2; ++v) {
+      const int n = n0 + 8 * y + 2 * t + v;
+      if (n >= nb || (done && done[n])) continue;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int i = i0 + 8 * x + g;
+        if (i < nc) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * c[x][y][v];
+      }
     }
-  }
 }
 
 // x += P Cv on the interior points (bilinear; the rim of Cv is zero, which is the Dirichlet condition of the correction).
-// Thread = 2 consecutive radial points (16 bytes in fp64), block = 128 x 2 points... one row segment of 256 points.
+// Thread = one 8-point radial segment of one row (it lies inside one coarse cell: HR = 16): the correction is linear along
+// it, base + slope * e, from the four coarse values of the cell interpolated in z.  64 bytes read and written per thread.
 template <class T>
-__global__ void __launch_bounds__(128) prolong_add_kernel(T* __restrict__ x, const double* __restrict__ Cv, const int* __restrict__ done,
+__global__ void __launch_bounds__(256) prolong_add_kernel(T* __restrict__ x, const double* __restrict__ Cv, const int* __restrict__ done,
                                                           int nx, int ny, int px, int pzpx) {
-  const int n = blockIdx.z, j = blockIdx.y;
-  if (j < 1 || j > ny - 2 || (done && done[n])) return;
-  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= nx) return;
+  const int n = blockIdx.z;
+  if (done && done[n]) return;
+  const int nseg = (nx + 7) / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = idx / nseg, sgm = idx % nseg;
+  if (j < 1 || j > ny - 2) return;
   const double* cv = Cv + (size_t)n * pzpx;
-  const int q0 = j / HZ; const double tz = (double)(j % HZ) * (1.0 / HZ);
-  T* row = x + ((size_t)n * ny + j) * nx;
+  const int q0 = j / HZ, p0 = sgm / 2; const double tz = (double)(j % HZ) * (1.0 / HZ);
+  cv += COL0;
+  const double c00 = cv[q0 * px + p0], c01 = cv[q0 * px + p0 + 1], c10 = cv[(q0 + 1) * px + p0], c11 = cv[(q0 + 1) * px + p0 + 1];
+  const double vl = fma(tz, c10 - c00, c00), vr = fma(tz, c11 - c01, c01);
+  const double sl = (vr - vl) * (1.0 / HR), base = fma(sl, (double)(8 * (sgm & 1)), vl);
+  T* row = x + ((size_t)n * ny + j) * nx + 8 * sgm;
+  if (8 * sgm + 8 <= nx - 1 && sgm > 0 && sizeof(T) == 8) {      // whole segment interior: vector accesses
+    double2* r2 = reinterpret_cast<double2*>(row);
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int ii = i + e;
-    if (ii < 1 || ii > nx - 2) continue;
-    const int p0 = ii / HR; const double tr = (double)(ii % HR) * (1.0 / HR);
-    const double c00 = cv[q0 * px + p0], c01 = cv[q0 * px + p0 + 1], c10 = cv[(q0 + 1) * px + p0], c11 = cv[(q0 + 1) * px + p0 + 1];
-    const double lo = fma(tr, c01 - c00, c00), hi = fma(tr, c11 - c10, c10);
-    row[ii] = (T)((double)row[ii] + fma(tz, hi - lo, lo));
+    for (int qd = 0; qd < 4; ++qd) {
+      double2 v = r2[qd];
+      v.x += fma(sl, (double)(2 * qd), base); v.y += fma(sl, (double)(2 * qd + 1), base);
+      r2[qd] = v;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = 8 * sgm + e;
+      if (i >= 1 && i <= nx - 2) row[e] = (T)((double)row[e] + fma(sl, (double)e, base));
+    }
   }
 }
 
