@@ -517,8 +517,12 @@ struct Plan : PlanBase {
     const int nt = ln_tiles_x * ln_tiles_y;
     tl::coarse_gather_kernel<<<nb, 256, 0, s>>>(tl_part, tl_rc, done, nt, ln_tiles_x, ln_tiles_y, tld.ncx, tld.ncz, tld.ncp);
     XEE_LAUNCH_OK();
-    tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 128, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc,
-                                                                                         tld.ncp, tld.ncx, tld.px, tld.pz * tld.px);
+    if (nb <= 4)
+      tl::coarse_matvec_kernel<<<dim3((tld.nc + 7) / 8, nb), 256, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
+                                                                       tld.px, tld.pz * tld.px);
+    else
+      tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 128, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc,
+                                                                                           tld.ncp, tld.ncx, tld.px, tld.pz * tld.px);
     XEE_LAUNCH_OK();
     return 0;
   }

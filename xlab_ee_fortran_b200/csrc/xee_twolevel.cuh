@@ -188,6 +188,21 @@ static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* _
     }
 }
 
+// The same product for a handful of solves (the spectral probes run on 1 solve): one warp per coarse unknown i, lanes over k,
+// shuffle reduction (the DMMA kernel would walk its 128 k-steps with 4 warps: ~50 us of pure latency).
+static __global__ void __launch_bounds__(256) coarse_matvec_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
+                                                                   double* __restrict__ Cv, const int* __restrict__ done, double scale,
+                                                                   int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, n = blockIdx.y;
+  if (i >= nc || (done && done[n])) return;
+  const double* ar = Ainv + (size_t)i * ncp; const double* rc = Rc + (size_t)n * ncp;
+  double t = 0.0;
+  for (int k = lane; k < ncp; k += 32) t = fma(ar[k], rc[k], t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * t;
+}
+
 // x += P Cv on the interior points (bilinear; the rim of Cv is zero, which is the Dirichlet condition of the correction).
 // Thread = one 8-point radial segment of one row (it lies inside one coarse cell: HR = 16): the correction is linear along
 // it, base + slope * e, from the four coarse values of the cell interpolated in z.  64 bytes read and written per thread.
