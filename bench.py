@@ -10,10 +10,12 @@ built on the device, all solves to tolerance, energy integrals, efficiency table
   python bench.py --gpus N --steps K --warmup W          # ours (one process per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host cores
 
-Method (`--method`, default line_chebyshev): Chebyshev-accelerated block-line relaxation (v5 kernel; same residual, tolerance
-and stop rule as solve_elliptic, 32-point radial blocks solved inside the sweep); `chebyshev` = accelerated point Jacobi on
-the temporally blocked kernel (v4); `jacobi` = the reference iteration.  Results of all three agree within the north_star
-tolerances (tests/test_gpu_map.py, tests/test_gpu_line.py).
+Method (`--method`, default line2_chebyshev): Chebyshev-accelerated TWO-LEVEL block-line relaxation (v5 kernel: 32-point radial
+blocks solved inside the sweep, plus a Galerkin coarse-grid correction on a 16 x 16-spaced bilinear space whose prolongation
+is fused into the sweep kernel; same residual, tolerance and stop rule as solve_elliptic); `line_chebyshev` = the one-level
+block-line method (the pure streaming kernel, last round's default; series workload default); `chebyshev` = accelerated point
+Jacobi on the temporally blocked kernel (v4); `jacobi` = the reference iteration.  Results of all four agree within the
+north_star tolerances (tests/test_gpu_map.py, tests/test_gpu_line.py, tests/test_gpu_twolevel.py).
 
 Workloads (`--workload`): `map` (default, above) and `series` = BASELINE config 5: `--nsnap` snapshots per GPU (default 128;
 8 GPUs = the 1024-snapshot series) with ONE OPERATOR PER SOLVE (varying wind profile / Ekman pumping), thermal + dynamical
@@ -318,8 +320,8 @@ def run_ours(args):
     interior = (NR - 2) * (NZ - 2)
     cheb = args.method.endswith("chebyshev"); line = args.method.startswith("line")
     fields = 4 if cheb else 3                                      # psi read, psi write, f read (+ psi_{k-1} for Chebyshev)
-    if args.method.startswith("line2"):
-        fields += 2                                                # + the prolongation pass of the coarse correction (psi read + write)
+    # (two-level method: the coarse correction adds no field pass - its prolongation is fused into the sweep kernel; its own
+    #  traffic, 32 doubles per tile and solve out and two 3 x 8 coarse patches in, is ~0.7 B per point and left out)
     opw = (13 if line else 9)                                      # operator words per point: 9 coefficients (+ m, u and 4 float planes)
     b_alg = 8.0 * (fields + (opw if series else opw / nloc))       # one operator per solve: it streams with every sweep
     alg_bytes = float(tab[:, 0].sum()) * interior * b_alg * args.steps
@@ -431,7 +433,7 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 # the reference arm (--impl reference) runs the reference's plain Jacobi, extrapolated: not the same iteration
                 "same_config": False,
-                "same_config_note": "GPU arm: Chebyshev-accelerated block-line relaxation to the same residual tolerance; reference arm: "
+                "same_config_note": "GPU arm: Chebyshev-accelerated (two-level) block-line relaxation to the same residual tolerance; reference arm: "
                                     "plain Jacobi (the reference's algorithm), a timed sample extrapolated to its sweep count; see like_for_like "
                                     "for the same-algorithm ratio",
                 "like_for_like": lfl,
@@ -452,7 +454,8 @@ def main():
     ap.add_argument("--nheat", type=int, default=512, help="map: heating locations (independent solves) per GPU")
     ap.add_argument("--nsnap", type=int, default=128, help="series: snapshots (independent solves, one operator each) per GPU")
     ap.add_argument("--total", type=int, default=0, help="fix the TOTAL number of locations / snapshots (strong scaling); 0 = per-GPU count x GPUs")
-    ap.add_argument("--method", default="line_chebyshev", choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi", "line2_chebyshev"])
+    ap.add_argument("--method", default=None, choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi", "line2_chebyshev"],
+                    help="default: line2_chebyshev for the map workload, line_chebyshev for the series (one operator per solve)")
     ap.add_argument("--check-step", type=int, default=0,
                     help="sweeps between residual checks (solve_elliptic's check_step); 0 = 100 for the point methods, 25 for the "
                          "line methods, which need ~4x fewer sweeps, 10 for the two-level method (a solve stops at the 2nd consecutive "
@@ -464,6 +467,8 @@ def main():
     ap.add_argument("--lfl-sweeps", type=int, default=300, help="GPU STRICT Jacobi sweeps timed for like_for_like")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.method is None:
+        args.method = "line_chebyshev" if args.workload == "series" else "line2_chebyshev"
     if args.check_step <= 0:
         args.check_step = 10 if args.method.startswith("line2") else 25 if args.method.startswith("line") else 100
     args.per_gpu = args.nsnap if args.workload == "series" else args.nheat

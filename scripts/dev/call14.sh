@@ -1,0 +1,10 @@
+export XEE_NO_BUILD=1
+for m in line2_chebyshev; do
+for v in "" _v4 _v5 _v2 ""; do
+  export XEE_SO=$PWD/xlab_ee_fortran_b200/lib/libxee_b200$v.so
+  timeout 200 python bench.py --steps 3 --warmup 1 --no-cpu --e2e-steps 0 --method $m 2>/dev/null | python -c "
+import sys, json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$m variant[$v]', round(d['value'],1), round(d['roofline']['avg_launch_us'],1), round(d['roofline']['frac'],3), d['roofline']['sweeps_per_solve'], d['clocks']['sm_mhz'])"
+done; done
+export XEE_SO=$PWD/xlab_ee_fortran_b200/lib/libxee_b200_v5.so
+timeout 200 python -m pytest tests/test_gpu_twolevel.py -x -q 2>&1 | tail -3

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
-SO = os.path.join(LIBDIR, "libxee_b200.so")
+SO = os.environ.get("XEE_SO") or os.path.join(LIBDIR, "libxee_b200.so")     # XEE_SO: load a variant build (kernel experiments)
 HEADER = os.path.join(_ROOT, "include", "xee_b200.h")
 
 NVCC_FLAGS = [

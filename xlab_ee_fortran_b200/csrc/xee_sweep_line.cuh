@@ -318,28 +318,32 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
   const size_t nn = (size_t)a.field_stride;
 
   // ---- prefetch cursor (thread 0): the same (unit, solve) sequence as the consumers, NSTAGE items ahead
-  int pu = blockIdx.x, pn = -1;
+  // (the unit -> (chunk, tile row, tile column) divisions happen once per unit: thread 0's warp is the one the others wait for)
+  int pu = (int)blockIdx.x - (int)gridDim.x, pn = 0, pn1 = 0, ptx = 0, pty = 0;
   uint32_t issued = 0;
   auto issue_next = [&]() {
     for (;;) {
-      if (pu >= nunits) return false;
-      const int ch = pu / ntiles;
-      const int n0 = ch * a.chunk, n1 = min(n0 + a.chunk, a.nbatch);
-      if (pn < 0) pn = n0; else ++pn;
-      if (pn >= n1) { pu += gridDim.x; pn = -1; continue; }
-      if (is_done(pn)) continue;
-      const int tile = pu % ntiles;
-      const int i0 = (tile % a.tiles_x) * TW, j0 = (tile / a.tiles_x) * TH;
+      if (pn >= pn1) {                         // next unit of this CTA
+        if (pu < nunits) pu += gridDim.x;
+        if (pu >= nunits) return false;
+        const int ch = pu / ntiles, tile = pu - ch * ntiles;
+        pn = ch * a.chunk; pn1 = min(pn + a.chunk, a.nbatch);
+        pty = tile / a.tiles_x; ptx = tile - pty * a.tiles_x;
+        continue;
+      }
+      const int n = pn++;
+      if (is_done(n)) continue;
+      const int i0 = ptx * TW, j0 = pty * TH;
       const int s = issued % NSTAGE;
       unsigned char* st = smem_raw + (size_t)s * SB;
       mbar_expect_tx(&full_bar[s], (uint32_t)(C::X_RAW + (CHEB ? 2 : 1) * C::F_RAW + (TWO ? (CHEB ? 2 : 1) * C::CP_RAW : 0)));
       if (TWO) {   // coarse patches: nodes 4 tx - 1 .. 4 tx + 6 (node p sits in column p + 1), coarse rows ty - 1 .. ty + 1
-        tma_load_3d(st + C::STAGE_BYTES, &map_cv, 4 * (tile % a.tiles_x), tile / a.tiles_x - 1, a.cv_cur_z + pn, &full_bar[s]);
-        if (CHEB) tma_load_3d(st + C::STAGE_BYTES + 256, &map_cv, 4 * (tile % a.tiles_x), tile / a.tiles_x - 1, a.cv_prev_z + pn, &full_bar[s]);
+        tma_load_3d(st + C::STAGE_BYTES, &map_cv, 4 * ptx, pty - 1, a.cv_cur_z + n, &full_bar[s]);
+        if (CHEB) tma_load_3d(st + C::STAGE_BYTES + 256, &map_cv, 4 * ptx, pty - 1, a.cv_prev_z + n, &full_bar[s]);
       }
-      tma_load_3d(st, &map_x, i0 - V, j0 - 1, pn, &full_bar[s]);
-      tma_load_3d(st + C::X_BYTES, &map_f, i0, j0, pn, &full_bar[s]);
-      if (CHEB) tma_load_3d(st + C::X_BYTES + C::F_BYTES, &map_xm, i0, j0, pn, &full_bar[s]);
+      tma_load_3d(st, &map_x, i0 - V, j0 - 1, n, &full_bar[s]);
+      tma_load_3d(st + C::X_BYTES, &map_f, i0, j0, n, &full_bar[s]);
+      if (CHEB) tma_load_3d(st + C::X_BYTES + C::F_BYTES, &map_xm, i0, j0, n, &full_bar[s]);
       ++issued;
       return true;
     }

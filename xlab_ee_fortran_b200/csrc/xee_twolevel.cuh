@@ -144,33 +144,35 @@ static __global__ void coarse_gather_kernel(const double* __restrict__ part, dou
 // on the FP64 tensor cores (mma.sync m8n8k4: DMMA).  Both operands are k-contiguous in memory, which is exactly the
 // row-major A / column-major B fragment layout of the instruction (thread (g = lane/4, t = lane%4) holds A[g][t] and
 // B[t][g]), so the fragments are loaded straight from global memory (2 MB + 2 MB, L2-resident, re-use through L1) with no
-// shared-memory staging.  Warp tile 32 (i) x 16 (n) = 4 x 2 accumulator fragments, block = 4 warps = 64 x 32.  Ainv and Rc
+// shared-memory staging.  Ainv and Rc
 // are padded to ncp (multiple of 64) with zeros: no edge handling in k or i; rows n >= nbatch are clamped and discarded.
 // Written into the rimmed layout Cv[n][pz][px] (interior only).
-constexpr int GM = 64, GN = 32;
+constexpr int GM = 32, GN = 32;
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
                                                                  double* __restrict__ Cv, const int* __restrict__ done, double scale,
                                                                  int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  // warp tile 16 (i) x 16 (n) = 2 x 2 accumulator fragments, block = 4 warps = 32 x 32: ncp/32 x nbatch/32 blocks (256 for the
+  // bench batch), i.e. several warps per SM sub-partition to hide the load latency of the k loop
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int i0 = blockIdx.x * GM + (warp & 1) * 32, n0 = blockIdx.y * GN + (warp >> 1) * 16;
-  double c[4][2][2] = {};
-  const double* ap[4]; const double* bp[2];
+  const int i0 = blockIdx.x * GM + (warp & 1) * 16, n0 = blockIdx.y * GN + (warp >> 1) * 16;
+  double c[2][2][2] = {};
+  const double* ap[2]; const double* bp[2];
 #pragma unroll
-  for (int x = 0; x < 4; ++x) ap[x] = Ainv + (size_t)(i0 + 8 * x + g) * ncp + t;
+  for (int x = 0; x < 2; ++x) ap[x] = Ainv + (size_t)(i0 + 8 * x + g) * ncp + t;
 #pragma unroll
   for (int y = 0; y < 2; ++y) bp[y] = Rc + (size_t)min(n0 + 8 * y + g, nb - 1) * ncp + t;
-#pragma unroll 8
+#pragma unroll 16
   for (int k0 = 0; k0 < ncp; k0 += 4) {
-    double a[4], b[2];
+    double a[2], b[2];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) a[x] = __ldg(ap[x] + k0);
+    for (int x = 0; x < 2; ++x) a[x] = __ldg(ap[x] + k0);
 #pragma unroll
     for (int y = 0; y < 2; ++y) b[y] = __ldg(bp[y] + k0);
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < 2; ++x)
 #pragma unroll
       for (int y = 0; y < 2; ++y) dmma_m8n8k4(c[x][y], a[x], b[y]);
   }
@@ -181,7 +183,7 @@ static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* _
       const int n = n0 + 8 * y + 2 * t + v;
       if (n >= nb || (done && done[n])) continue;
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
+      for (int x = 0; x < 2; ++x) {
         const int i = i0 + 8 * x + g;
         if (i < nc) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * c[x][y][v];
       }
