@@ -193,6 +193,7 @@ struct Plan : PlanBase {
   tl::Dims tld{};
   double *tl_ainv = nullptr, *tl_tmp = nullptr;   // [ncp][ncp]: Ac^-1 (and the second Gauss-Jordan buffer)
   double *tl_part = nullptr;                      // [nbatch][ntiles][32] per-tile restriction of the residual
+  double *tl_ck = nullptr;                        // [GSPLIT][nbatch][ncp] partial products of the coarse solve
   double *tl_rc = nullptr, *tl_cv = nullptr;      // [nbatch][ncp] restricted residual, [2 slots][nbatch][pz][px] coarse corrections
   CUtensorMap map_cv{};                           //   ... and the TMA view of them ({px, pz, 2 nbatch}, boxes of 8 x 3)
   double tl_gamma = 1.0, tl_lmax = 0.0, tl_lmin = 0.0;
@@ -308,6 +309,7 @@ struct Plan : PlanBase {
         XEE_CHECK(pool_alloc(&tl_ainv, ab)); XEE_CHECK(pool_alloc(&tl_tmp, ab));
         XEE_CHECK(pool_alloc(&tl_part, sizeof(double) * (size_t)nb * nt * 32));
         XEE_CHECK(pool_alloc(&tl_rc, sizeof(double) * (size_t)nb * tld.ncp));
+        XEE_CHECK(pool_alloc(&tl_ck, sizeof(double) * tl::GSPLIT * (size_t)nb * tld.ncp));
         XEE_CHECK(pool_alloc(&tl_cv, sizeof(double) * 2 * (size_t)nb * tld.pz * tld.px));
         XEE_CHECK(cudaMemsetAsync(tl_rc, 0, sizeof(double) * (size_t)nb * tld.ncp, own_stream));                 // padding stays 0
         XEE_CHECK(cudaMemsetAsync(tl_cv, 0, sizeof(double) * 2 * (size_t)nb * tld.pz * tld.px, own_stream));     // rim stays 0
@@ -430,7 +432,7 @@ struct Plan : PlanBase {
     // The pool recycles blocks without stream tracking: make sure no kernel of this plan (or of a caller's stream that used
     // its buffers: apply / eta / uw return without synchronising) still touches them before they go back on the free list.
     cudaDeviceSynchronize();
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_cv); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_ck); pool_free(tl_cv); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -520,9 +522,12 @@ struct Plan : PlanBase {
     if (nb <= 4)
       tl::coarse_matvec_kernel<<<dim3((tld.nc + 7) / 8, nb), 256, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
                                                                        tld.px, tld.pz * tld.px);
-    else
-      tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN), 128, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc,
-                                                                                           tld.ncp, tld.ncx, tld.px, tld.pz * tld.px);
+    else {
+      tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN, tl::GSPLIT), 128, 0, s>>>(tl_ainv, tl_rc, tl_ck, nb, tld.ncp);
+      XEE_LAUNCH_OK();
+      tl::coarse_finish_kernel<<<dim3((tld.nc + 127) / 128, nb), 128, 0, s>>>(tl_ck, two_cv(slot, nb), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
+                                                                           tld.px, tld.pz * tld.px);
+    }
     XEE_LAUNCH_OK();
     return 0;
   }

@@ -151,21 +151,22 @@ constexpr int GM = 32, GN = 32;
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+constexpr int GSPLIT = 4;   // the k range is split over GSPLIT blocks (more warps in flight: the loop is latency-bound), partial
+                            // products summed in a fixed order by coarse_finish_kernel (deterministic, no atomics)
 static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
-                                                                 double* __restrict__ Cv, const int* __restrict__ done, double scale,
-                                                                 int nb, int nc, int ncp, int ncx, int px, int pzpx) {
-  // warp tile 16 (i) x 16 (n) = 2 x 2 accumulator fragments, block = 4 warps = 32 x 32: ncp/32 x nbatch/32 blocks (256 for the
-  // bench batch), i.e. several warps per SM sub-partition to hide the load latency of the k loop
+                                                                 double* __restrict__ Ck, int nb, int ncp) {
+  // warp tile 16 (i) x 16 (n) = 2 x 2 accumulator fragments, block = 4 warps = 32 x 32; grid (ncp/32, nbatch/32, GSPLIT)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int i0 = blockIdx.x * GM + (warp & 1) * 16, n0 = blockIdx.y * GN + (warp >> 1) * 16;
+  const int klen = ncp / GSPLIT, kbeg = blockIdx.z * klen;      // ncp is a multiple of 64
   double c[2][2][2] = {};
   const double* ap[2]; const double* bp[2];
 #pragma unroll
-  for (int x = 0; x < 2; ++x) ap[x] = Ainv + (size_t)(i0 + 8 * x + g) * ncp + t;
+  for (int x = 0; x < 2; ++x) ap[x] = Ainv + (size_t)(i0 + 8 * x + g) * ncp + kbeg + t;
 #pragma unroll
-  for (int y = 0; y < 2; ++y) bp[y] = Rc + (size_t)min(n0 + 8 * y + g, nb - 1) * ncp + t;
+  for (int y = 0; y < 2; ++y) bp[y] = Rc + (size_t)min(n0 + 8 * y + g, nb - 1) * ncp + kbeg + t;
 #pragma unroll 16
-  for (int k0 = 0; k0 < ncp; k0 += 4) {
+  for (int k0 = 0; k0 < klen; k0 += 4) {
     double a[2], b[2];
 #pragma unroll
     for (int x = 0; x < 2; ++x) a[x] = __ldg(ap[x] + k0);
@@ -176,18 +177,26 @@ static __global__ void __launch_bounds__(128) coarse_gemm_kernel(const double* _
 #pragma unroll
       for (int y = 0; y < 2; ++y) dmma_m8n8k4(c[x][y], a[x], b[y]);
   }
+  double* out = Ck + (size_t)blockIdx.z * nb * ncp;
 #pragma unroll
   for (int y = 0; y < 2; ++y)
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int n = n0 + 8 * y + 2 * t + v;
-      if (n >= nb || (done && done[n])) continue;
+      if (n >= nb) continue;
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        const int i = i0 + 8 * x + g;
-        if (i < nc) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * c[x][y][v];
-      }
+      for (int x = 0; x < 2; ++x) out[(size_t)n * ncp + i0 + 8 * x + g] = c[x][y][v];
     }
+}
+// Cv[n][node] = scale * (sum of the GSPLIT partial products), written into the rimmed layout (interior only).
+static __global__ void coarse_finish_kernel(const double* __restrict__ Ck, double* __restrict__ Cv, const int* __restrict__ done,
+                                            double scale, int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  const int n = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc || (done && done[n])) return;
+  double t = 0.0;
+#pragma unroll
+  for (int q = 0; q < GSPLIT; ++q) t += Ck[((size_t)q * nb + n) * ncp + i];
+  Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * t;
 }
 
 // The same product for a handful of solves (the spectral probes run on 1 solve): one warp per coarse unknown i, lanes over k,
