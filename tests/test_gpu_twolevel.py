@@ -114,7 +114,52 @@ def test_line2_rejects_what_it_cannot_do():
     with pytest.raises(RuntimeError, match="two-level"):
         X.Plan(16, 16, nbatch=2, dtype="f64", shared_coe=True, arith="fast", method="line2_chebyshev")     # no coarse node
     with pytest.raises(RuntimeError, match="two-level"):
-        X.Plan(64, 48, nbatch=2, dtype="f64", shared_coe=False, arith="fast", method="line2_chebyshev")    # one operator per solve
+        X.Plan(64, 48, nbatch=2, dtype="f32", shared_coe=True, arith="fast", method="line2_chebyshev")     # fp64 fields only
+
+
+@pytest.mark.parametrize("shape,nb", [((128, 72), 3), ((200, 56), 5)])
+def test_line2_one_operator_per_solve_matches_numpy_restatement(shape, nb):
+    """Time-series layout: every solve has its own operator, hence its own Galerkin coarse operator and inverse."""
+    torch, X, O = _mods()
+    nx, ny = shape
+    coes, Fs, Ps = [], [], []
+    for k in range(nb):
+        a, b, c, F, P = _batch(nx, ny, 1, np.float64, seed=100 + 7 * k)
+        coes.append(O.cal_coe(a * (1.0 + 0.2 * k), b, c, 1.0, 0.5, nx, ny)[0]); Fs.append(F[0]); Ps.append(P[0])
+    coe = np.stack(coes); F = np.stack(Fs); P = np.stack(Ps)
+    plan = X.Plan(nx, ny, nbatch=nb, dtype="f64", shared_coe=False, arith="fast", method="line2_jacobi")
+    plan.set_coe_aos(coe)
+    psi = torch.from_numpy(P).cuda(); ft = torch.from_numpy(F).cuda()
+    plan.sweeps(psi, ft, 0.45, 3)
+    plan.close()
+    got = psi.cpu().numpy()
+    for k in range(nb):
+        ref, _ = TwoLevel(coe[k]).jacobi(P[k], F[k], 0.45, 3)
+        assert rel_l2(got[k], ref) < 1e-11, (k, rel_l2(got[k], ref))
+
+
+def test_series_with_the_two_level_method():
+    """BASELINE config 5 chain (one operator per snapshot) with the two-level method against the one-level block-line method:
+    same tables to the tolerances of the solve, far fewer sweeps."""
+    import xlab_ee_fortran_b200 as X
+    from xlab_ee_fortran_b200 import workloads as W
+    from xlab_ee_fortran_b200.time_series import TimeSeries
+    nr, nz, ns = 256, 128, 6
+    Lr, Lz = (0.0, 1.0e6), (0.0, 1.5e4)
+    params = W.series_params(ns, total=64, first=5)
+    tabs = {}; psis = {}
+    for method, cs in (("line_chebyshev", 25), ("line2_chebyshev", 10)):
+        ts = TimeSeries(nr, nz, Lr, Lz, ns, "f64", arith="fast", method=method, r1_rel=1e-11)
+        tabs[method] = ts.run(params, X.SolveParams(max_iter=400000, check_step=cs, converge_time=2, r1=1.0, r2=0.0, stall_checks=20))
+        psis[method] = ts.field("psi")
+        ts.close()
+    t0, t1 = tabs["line_chebyshev"], tabs["line2_chebyshev"]
+    print("sweeps one-level", t0[:, 0], "two-level", t1[:, 0])
+    assert np.all(t1[:, 2] == 0) and np.all(t0[:, 2] == 0)
+    for k in range(ns):
+        assert rel_l2(psis["line2_chebyshev"][k], psis["line_chebyshev"][k]) < 1e-8
+    assert np.allclose(t1[:, 5], t0[:, 5], rtol=1e-6) and np.allclose(t1[:, 6:], t0[:, 6:], rtol=1e-6)
+    assert t1[:, 0].max() * 1.5 <= t0[:, 0].min()
 
 
 def test_efficiency_map_with_the_two_level_method():

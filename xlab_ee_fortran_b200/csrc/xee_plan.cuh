@@ -151,6 +151,8 @@ struct PlanBase {
   long long kernel_launches = 0;     // launches of the sweep kernel
   int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..5) and its sweeps per pass
   double cheb_rho_used = 0.0, cheb_gamma_used = 1.0;   // Chebyshev parameters of the last accelerated call
+  int rho_subsample = 0;   // > 1 (one operator per solve): probe every rho_subsample-th operator set only and interpolate the
+                           // spectral data in between - for series whose operators vary smoothly with the index (set by the caller)
 };
 
 template <class T>
@@ -193,6 +195,8 @@ struct Plan : PlanBase {
   tl::Dims tld{};
   double *tl_ainv = nullptr, *tl_tmp = nullptr;   // [ncp][ncp]: Ac^-1 (and the second Gauss-Jordan buffer)
   double *tl_part = nullptr;                      // [nbatch][ntiles][32] per-tile restriction of the residual
+  double *tl_band = nullptr;                      // [nsets][2][nc][ncx + 2] band LU factors of the coarse operators
+  double *tl_scale = nullptr;                     // [nbatch] per-solve factor of the coarse correction (one operator per solve)
   double *tl_ck = nullptr;                        // [GSPLIT][nbatch][ncp] partial products of the coarse solve
   double *tl_rc = nullptr, *tl_cv = nullptr;      // [nbatch][ncp] restricted residual, [2 slots][nbatch][pz][px] coarse corrections
   CUtensorMap map_cv{};                           //   ... and the TMA view of them ({px, pz, 2 nbatch}, boxes of 8 x 3)
@@ -301,12 +305,13 @@ struct Plan : PlanBase {
       want = 5;
       if (use_two) {
         static_assert(ln::TH == tl::HZ && 2 * ln::SEG == tl::HR, "the two-level restriction assumes 16-row tiles and two 8-point segments per coarse cell");
-        if (!d.shared_coe) return fail("xee: the two-level methods need a shared operator");
         if (sizeof(T) != 8) return fail("xee: the two-level methods need fp64 fields");
         tld = tl::dims(d.nx, d.ny);
         if (tld.ncx < 1 || tld.ncz < 1) return fail("xee: the two-level methods need at least 18 x 18 grid points (one coarse node)");
-        const size_t ab = sizeof(double) * (size_t)tld.ncp * tld.ncp;
+        const size_t ab = sizeof(double) * (size_t)tld.ncp * tld.ncp * nsets;     // one coarse operator per operator set
         XEE_CHECK(pool_alloc(&tl_ainv, ab)); XEE_CHECK(pool_alloc(&tl_tmp, ab));
+        XEE_CHECK(pool_alloc(&tl_scale, sizeof(double) * nb));
+        XEE_CHECK(pool_alloc(&tl_band, sizeof(double) * 2 * (size_t)tld.nc * (tld.ncx + 2) * nsets));
         XEE_CHECK(pool_alloc(&tl_part, sizeof(double) * (size_t)nb * nt * 32));
         XEE_CHECK(pool_alloc(&tl_rc, sizeof(double) * (size_t)nb * tld.ncp));
         XEE_CHECK(pool_alloc(&tl_ck, sizeof(double) * tl::GSPLIT * (size_t)nb * tld.ncp));
@@ -432,7 +437,7 @@ struct Plan : PlanBase {
     // The pool recycles blocks without stream tracking: make sure no kernel of this plan (or of a caller's stream that used
     // its buffers: apply / eta / uw return without synchronising) still touches them before they go back on the free list.
     cudaDeviceSynchronize();
-    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_ck); pool_free(tl_cv); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
+    { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_ck); pool_free(tl_cv); pool_free(tl_scale); pool_free(tl_band); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
       pool_free(partial);
@@ -492,21 +497,26 @@ struct Plan : PlanBase {
   int two_setup() {
     TraceTimer tt("two-level setup");
     const int nc = tld.nc, ncp = tld.ncp;
-    const size_t ab = sizeof(double) * (size_t)ncp * ncp;
+    const size_t ab = sizeof(double) * (size_t)ncp * ncp * nsets;
     XEE_CHECK(cudaMemsetAsync(tl_ainv, 0, ab, own_stream));
-    tl::galerkin_kernel<T><<<nc, 256, 0, own_stream>>>(coe, tl_ainv, d.nx, d.ny, tld.ncx, tld.ncz, ncp);
+    tl::galerkin_kernel<T><<<dim3(nc, nsets), 256, 0, own_stream>>>(coe, tl_ainv, d.nx, d.ny, tld.ncx, tld.ncz, ncp);
     XEE_LAUNCH_OK();
-    if (ncp > nc) { tl::pad_identity_kernel<<<(ncp - nc + 63) / 64, 64, 0, own_stream>>>(tl_ainv, nc, ncp); XEE_LAUNCH_OK(); }
+    if (ncp > nc) { tl::pad_identity_kernel<<<dim3((ncp - nc + 63) / 64, nsets), 64, 0, own_stream>>>(tl_ainv, nc, ncp); XEE_LAUNCH_OK(); }
+    // band LU of every Ac (half-bandwidth ncx + 1), then the dense inverse column by column (tl_tmp holds Ac, tl_ainv the inverse)
+    const int bw = tld.ncx + 1;
     XEE_CHECK(cudaMemcpyAsync(tl_tmp, tl_ainv, ab, cudaMemcpyDeviceToDevice, own_stream));
-    double *src = tl_ainv, *dst = tl_tmp;
-    const dim3 g((nc + 127) / 128, nc);
-    for (int k = 0; k < nc; ++k) {
-      tl::gj_step_kernel<<<g, 128, 0, own_stream>>>(src, dst, nc, ncp, k);
-      std::swap(src, dst);
+    {
+      static std::atomic<unsigned long long> attr_done{0};
+      const int smem = (bw + 1) * (2 * bw + 1) * (int)sizeof(double);
+      if (smem > 200 * 1024) return fail("xee: two-level: coarse grid too wide for the band factorisation");
+      if (opt_in_smem(tl::band_lu_kernel, std::max(smem, 48 * 1024), attr_done)) return 1;
+      tl::band_lu_kernel<<<nsets, 1024, smem, own_stream>>>(tl_tmp, tl_band, nc, ncp, bw);
+      XEE_LAUNCH_OK();
     }
-    g_launches.fetch_add(nc, std::memory_order_relaxed);
-    XEE_CHECK(cudaGetLastError());
-    if (src != tl_ainv) XEE_CHECK(cudaMemcpyAsync(tl_ainv, src, ab, cudaMemcpyDeviceToDevice, own_stream));
+    XEE_CHECK(cudaMemsetAsync(tl_ainv, 0, ab, own_stream));
+    if (ncp > nc) { tl::pad_identity_kernel<<<dim3((ncp - nc + 63) / 64, nsets), 64, 0, own_stream>>>(tl_ainv, nc, ncp); XEE_LAUNCH_OK(); }
+    tl::band_inverse_kernel<<<dim3((nc + 127) / 128, nsets), 128, 0, own_stream>>>(tl_band, tl_ainv, nc, ncp, bw);
+    XEE_LAUNCH_OK();
     XEE_CHECK(cudaStreamSynchronize(own_stream));
     tl_ready = true; tl_lmax = tl_lmin = 0.0; tl_gamma = 1.0;
     return 0;
@@ -515,17 +525,25 @@ struct Plan : PlanBase {
   // batch, scaled by `scale` = -omega gamma, written as the coarse correction c of the NEW iterate (slot `slot`).  The fields
   // are not touched: psi = y + P c is formed by whoever reads them (the next sweep; two_flush at the end).
   double* two_cv(int slot, int nb) const { return tl_cv + (size_t)slot * nb * tld.pz * tld.px; }
-  int two_coarse(int slot, int nb, double scale, const int* done, cudaStream_t s) {
+  int two_coarse(int slot, int nb, double scale, const T* rho_ps_dev, int cheb_k, const int* done, cudaStream_t s) {
     const int nt = ln_tiles_x * ln_tiles_y;
     tl::coarse_gather_kernel<<<nb, 256, 0, s>>>(tl_part, tl_rc, done, nt, ln_tiles_x, ln_tiles_y, tld.ncx, tld.ncz, tld.ncp);
     XEE_LAUNCH_OK();
-    if (nb <= 4)
-      tl::coarse_matvec_kernel<<<dim3((tld.nc + 7) / 8, nb), 256, 0, s>>>(tl_ainv, tl_rc, two_cv(slot, nb), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
+    if (!d.shared_coe || nb <= 4) {
+      // one coarse operator per solve (time series), or a handful of solves (spectral probes): a matrix-vector product per solve
+      const double* sps = nullptr;
+      if (rho_ps_dev) {
+        tl::coarse_scale_kernel<T><<<(nb + 127) / 128, 128, 0, s>>>(rho_ps_dev, cheb_k, tl_gamma, tl_scale, nb);
+        XEE_LAUNCH_OK();
+        sps = tl_scale;
+      }
+      tl::coarse_matvec_kernel<<<dim3((tld.nc + 7) / 8, nb), 256, 0, s>>>(tl_ainv, d.shared_coe ? 0 : (long long)tld.ncp * tld.ncp, tl_rc,
+                                                                       two_cv(slot, d.nbatch), done, scale, sps, nb, tld.nc, tld.ncp, tld.ncx,
                                                                        tld.px, tld.pz * tld.px);
-    else {
+    } else {
       tl::coarse_gemm_kernel<<<dim3(tld.ncp / tl::GM, (nb + tl::GN - 1) / tl::GN, tl::GSPLIT), 128, 0, s>>>(tl_ainv, tl_rc, tl_ck, nb, tld.ncp);
       XEE_LAUNCH_OK();
-      tl::coarse_finish_kernel<<<dim3((tld.nc + 127) / 128, nb), 128, 0, s>>>(tl_ck, two_cv(slot, nb), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
+      tl::coarse_finish_kernel<<<dim3((tld.nc + 127) / 128, nb), 128, 0, s>>>(tl_ck, two_cv(slot, d.nbatch), done, scale, nb, tld.nc, tld.ncp, tld.ncx,
                                                                            tld.px, tld.pz * tld.px);
     }
     XEE_LAUNCH_OK();
@@ -660,7 +678,7 @@ struct Plan : PlanBase {
     XEE_LAUNCH_OK();
     if (use_two) {   // psi' = psi - alpha (z + P E) (Jacobi) / y - omega gamma P E (Chebyshev; omega from the per-launch value)
       const double scale = mode == MODE_CHEBYSHEV ? -(double)a.omega * tl_gamma : -(double)a.alpha;
-      return two_coarse(1 - a.two_slot, d.nbatch, scale, a.done, s);
+      return two_coarse(1 - a.two_slot, a.nbatch, scale, mode == MODE_CHEBYSHEV ? a.rho_ps : nullptr, a.cheb_k, a.done, s);
     }
     return 0;
   }
@@ -791,6 +809,8 @@ struct Plan : PlanBase {
   }
   int solve_resident(T* x0, const T* fd, const xee_solve_params* prm, int check_step, int converge_time, int lost_rate, int mode, cudaStream_t s);
   int estimate_rho(cudaStream_t s);
+  int estimate_rho_subsampled(cudaStream_t s);
+  std::vector<double> lmin_ps;       // two-level: per-set smallest eigenvalue of M^-1 L (host copy, for the subsampled estimate)
   // Make the Chebyshev parameters of this call available: explicit value, cached estimate, or a fresh estimate.
   int prepare_cheb(double rho_given, cudaStream_t s) {
     if (rho_given > 0 && !use_two) {   // (the two-level methods also need the step length: they always estimate)
@@ -804,7 +824,8 @@ struct Plan : PlanBase {
     if (cheb_rho > 0 && (int)rho_ps.size() == nsets) return 0;
     XEE_CHECK(cudaStreamSynchronize(s));
     const double t0 = TraceTimer::now();
-    const int rc = estimate_rho(s);      // synchronises the stream before it returns
+    const bool sub = !d.shared_coe && rho_subsample > 1 && nsets >= 4 * rho_subsample;
+    const int rc = sub ? estimate_rho_subsampled(s) : estimate_rho(s);      // synchronises the stream before it returns
     probe_ms += (TraceTimer::now() - t0) * 1e3;
     return rc;
   }
@@ -927,10 +948,12 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     const T* src = parity ? e1 : e0; T* dst = parity ? e0 : e1;
     SweepArgs<T> a = args(src, dst, zf, (T)(use_two ? tl_gamma : 1.0), T(1), nullptr);
     a.nbatch = ns; a.rho_ps = rho_dev; a.cheb_k = k;
-    if (use_two) {   // one shared operator: the host-computed weight goes to the sweep kernel AND scales the coarse correction
-      a.rho_ps = nullptr;
-      a.omega = mode == MODE_CHEBYSHEV ? (T)cheb_omega_host(k, (double)rho_h[0]) : T(1);
+    if (use_two) {
       a.two_slot = parity;                  // e0 owns coarse slot 0, e1 slot 1
+      if (d.shared_coe) {   // one shared operator: the host-computed weight goes to the sweep kernel AND scales the coarse correction
+        a.rho_ps = nullptr;
+        a.omega = mode == MODE_CHEBYSHEV ? (T)cheb_omega_host(k, (double)rho_h[0]) : T(1);
+      }                     // (one operator per solve: both take the weight of solve n from rho_dev[n])
     }
     parity ^= 1;
     return launch_sweep(a, mode, false, s);
@@ -951,22 +974,24 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     // non-negative, so its dominant mode is the smooth one the probes look for.
     for (int j = 1; j < d.ny - 1; ++j)
       for (int i = 1; i < d.nx - 1; ++i) h[(size_t)j * d.nx + i] *= (T)((j & 1) ? -1.0 : 1.0) * (T)(1.0 + 0.25 * std::sin(0.7 * i + 1.3 * j));
-    XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+    for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
     tl_gamma = 1.0;
-    const int itL = env_int("XEE_LMAX_ITERS", 60);
+    const int itL = env_int("XEE_LMAX_ITERS", ns > 1 ? 24 : 60);
     for (int k = 1; k <= itL && !rc; ++k) {
       const T* cur = parity ? e1 : e0;
       if (k == itL) rc = rc || norms(cur, nA);
       rc = rc || sweep(MODE_JACOBI, 1);                         // other = cur - M^-1 L cur   (parity now names `other`)
       rc = rc || flush();
       T* oth = parity ? e1 : e0; const T* was = parity ? e0 : e1;
-      tl::diff_kernel<T><<<256, 256, 0, s>>>(oth, was, nn);     // other = other - cur = -M^-1 L cur
+      tl::diff_kernel<T><<<1024, 256, 0, s>>>(oth, was, nn * ns);     // other = other - cur = -M^-1 L cur
       XEE_LAUNCH_OK();
       if (k == itL) rc = rc || norms(oth, nB);
     }
     if (rc) return 1;
-    tl_lmax = 1.02 * std::max(2.0, 1.01 * nB[0] / nA[0]);
+    double grow = 0.0;
+    for (int n = 0; n < ns; ++n) grow = std::max(grow, nA[n] > 0 ? nB[n] / nA[n] : 0.0);
+    tl_lmax = 1.02 * std::max(2.0, 1.01 * grow);      // one bound for every operator set: the step length gamma is common
     if (!(tl_lmax > 0.5 && tl_lmax < 8.0)) {
       char msg[200]; snprintf(msg, sizeof msg, "xee: two-level: largest eigenvalue estimate of M^-1 L out of range (%.6e)", tl_lmax);
       return fail(msg);
@@ -976,8 +1001,8 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     for (int j = 1; j < d.ny - 1; ++j)
       for (int i = 1; i < d.nx - 1; ++i)
         h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
-    XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn, cudaMemcpyDeviceToDevice, s));
+    for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
     parity = 0;
   }
   // ---- stage A
@@ -1035,10 +1060,15 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     if (all_settled) break;
   }
   if (rc) return 1;
-  if (use_two) {   // rho[0] is the spectral radius of I - gamma0 M^-1 L: lmin = (1 - rho) / gamma0, then the final step and radius
-    tl_lmin = (1.0 - rho[0]) / tl_gamma;
+  if (use_two) {   // rho[n] is the spectral radius of I - gamma0 M^-1 L_n: lmin_n = (1 - rho_n) / gamma0, then the final step and radii
+    // (one common step from the mean lmin; with it the spectrum of solve n lies in [1 - gamma lmax, 1 - gamma lmin_n])
+    std::vector<double> lmin(ns);
+    double mean = 0.0;
+    for (int n = 0; n < ns; ++n) { lmin[n] = (1.0 - rho[n]) / tl_gamma; mean += lmin[n] / ns; }
+    lmin_ps = lmin;
+    tl_lmin = mean;
     tl_gamma = 2.0 / (tl_lmax + tl_lmin);
-    rho[0] = (tl_lmax - tl_lmin) / (tl_lmax + tl_lmin);
+    for (int n = 0; n < ns; ++n) rho[n] = std::max(tl_gamma * tl_lmax - 1.0, 1.0 - tl_gamma * lmin[n]);
     if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: two-level spectrum of M^-1 L: [%.4e, %.4f], gamma %.4f\n", tl_lmin, tl_lmax, tl_gamma);
   }
   rho_ps = rho;
@@ -1047,6 +1077,58 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   XEE_CHECK(cudaStreamSynchronize(s));
   cheb_rho = rho[0];
   if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho[0] = 1 - %.4e (%d operator set%s)\n", 1.0 - rho[0], ns, ns > 1 ? "s" : "");
+  return 0;
+}
+
+// One operator per solve, operators varying smoothly with the solve index (a time series): the spectral probes run on every
+// rho_subsample-th operator set only (a small plan of its own holding copies of those operators), and the quantity that
+// drives the Chebyshev weights - the gap 1 - rho of the one-level methods, the smallest eigenvalue of M^-1 L of the two-level
+// ones - is interpolated (log-linearly in the index) for the sets in between.  A wrong value costs sweeps, not correctness:
+// the residual and the stop rule are those of every other method.
+template <class T>
+int Plan<T>::estimate_rho_subsampled(cudaStream_t s) {
+  TraceTimer tt("estimate_rho (subsampled)");
+  std::vector<int> idx;
+  for (int n = 0; n < nsets; n += rho_subsample) idx.push_back(n);
+  if (idx.back() != nsets - 1) idx.push_back(nsets - 1);
+  const int nq = (int)idx.size();
+  Plan<T> sub;
+  sub.d = d; sub.d.nbatch = nq; sub.d.shared_coe = 0; sub.d.kernel = 0;
+  if (sub.init()) return 1;
+  XEE_CHECK(cudaStreamSynchronize(s));
+  for (int q = 0; q < nq; ++q)
+    XEE_CHECK(cudaMemcpyAsync(sub.coe + (size_t)q * kPlanes * nn, coe + (size_t)idx[q] * kPlanes * nn, sizeof(T) * kPlanes * nn, cudaMemcpyDeviceToDevice, sub.own_stream));
+  XEE_CHECK(cudaStreamSynchronize(sub.own_stream));
+  if (sub.line_factors()) return 1;
+  if (sub.estimate_rho(sub.own_stream)) return 1;
+  // the interpolated quantity at the sampled sets
+  std::vector<double> v(nq);
+  for (int q = 0; q < nq; ++q) v[q] = use_two ? sub.lmin_ps[q] : 1.0 - sub.rho_ps[q];
+  for (int q = 0; q < nq; ++q)
+    if (!(v[q] > 0.0)) return fail("xee: subsampled spectral estimate: non-positive gap");
+  std::vector<double> rho(nsets), lmin(nsets);
+  double mean = 0.0;
+  for (int n = 0, q = 0; n < nsets; ++n) {
+    while (q + 1 < nq - 1 && idx[q + 1] <= n) ++q;
+    const double t = idx[q + 1] > idx[q] ? (double)(n - idx[q]) / (idx[q + 1] - idx[q]) : 0.0;
+    lmin[n] = std::exp((1.0 - t) * std::log(v[q]) + t * std::log(v[q + 1]));
+    mean += lmin[n] / nsets;
+  }
+  if (use_two) {
+    tl_lmax = sub.tl_lmax; tl_lmin = mean;
+    tl_gamma = 2.0 / (tl_lmax + tl_lmin);
+    for (int n = 0; n < nsets; ++n) rho[n] = std::max(tl_gamma * tl_lmax - 1.0, 1.0 - tl_gamma * lmin[n]);
+    lmin_ps = lmin;
+  } else {
+    for (int n = 0; n < nsets; ++n) rho[n] = 1.0 - lmin[n];
+  }
+  if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * nsets));
+  std::vector<T> rho_h(nsets);
+  for (int n = 0; n < nsets; ++n) rho_h[n] = (T)rho[n];
+  XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * nsets, cudaMemcpyHostToDevice, s));
+  XEE_CHECK(cudaStreamSynchronize(s));
+  rho_ps = rho; cheb_rho = rho[0];
+  if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: subsampled spectral estimate: %d of %d operator sets probed, gap[0] = %.4e, gap[last] = %.4e\n", nq, nsets, lmin[0], lmin[nsets - 1]);
   return 0;
 }
 

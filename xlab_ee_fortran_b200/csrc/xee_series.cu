@@ -214,6 +214,18 @@ struct Series : SeriesBase {
     series_m2_kernel<T><<<gm, 64, 0, s>>>(C, m2, ra, ra, nr, nz, nb); XEE_LAUNCH_OK();
     series_mom_rhs_kernel<T><<<gO, 128, 0, s>>>(snaps, m2, f, ra, ra, za, nr, nz); XEE_LAUNCH_OK();
     series_bc_kernel<T><<<gO, 128, 0, s>>>(snaps, psi, ra, nr, nz); XEE_LAUNCH_OK();
+    // Spectral probes of the accelerated methods: when the snapshots form a smooth series (every vortex parameter changes by
+    // less than 5 % from one snapshot to the next) only every 8th operator is probed and the rest interpolated.
+    {
+      double worst = 0.0;
+      for (int n = 1; n < nb; ++n)
+        for (int q = 0; q < 14; ++q) {
+          const double a0 = params[(size_t)(n - 1) * kSeriesCols + q], a1 = params[(size_t)n * kSeriesCols + q];
+          const double sc = std::max(std::fabs(a0), std::fabs(a1));
+          if (sc > 0) worst = std::max(worst, std::fabs(a1 - a0) / sc);
+        }
+      pl->rho_subsample = (nb >= 32 && worst < 0.05) ? env_int("XEE_RHO_SUBSAMPLE", 8) : 0;
+    }
     xee_solve_params prm = *prm_in;
     if (d.r1_rel_rms_f > 0) {
       // tolerance relative to the INITIAL residual L psi0 - f: with the pumping boundary condition the boundary data,

@@ -18,7 +18,8 @@
 // tensor cores), scaled by -omega_k gamma.  The prolongation P E is NOT a pass over the fields: the iterate is kept as
 // (stored field y, coarse vector c), psi = y + P c, and the sweep kernel adds P c to what it reads (xee_sweep_line.cuh);
 // prolong_add_kernel applies it once, when a solve ends.  Once per operator: galerkin_kernel assembles Ac (9-point coarse
-// stencil) and gj_step_kernel inverts it (Gauss-Jordan without pivoting: Ac is definite like L).
+// stencil, a banded matrix), band_lu_kernel factors the band (no pivoting: Ac is definite like L) and band_inverse_kernel
+// forms the dense inverse column by column.
 #pragma once
 #include "xee_kernels.cuh"
 
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const T* __restrict__ coe
   const int q = blockIdx.x, qx = q % ncx + 1, qz = q / ncx + 1;
   const int ic = HR * qx, jc = HZ * qz;
   const size_t nn = (size_t)nx * ny;
+  coe += (size_t)blockIdx.y * kPlanes * nn;            // operator set (one per solve for a time series)
+  Ac += (size_t)blockIdx.y * ncp * ncp;
   double acc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.0;
@@ -90,23 +93,70 @@ __global__ void __launch_bounds__(256) galerkin_kernel(const T* __restrict__ coe
 }
 static __global__ void pad_identity_kernel(double* __restrict__ A, int nc, int ncp) {
   const int k = nc + blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ncp) A[(size_t)k * ncp + k] = 1.0;
+  if (k < ncp) A[(size_t)blockIdx.y * ncp * ncp + (size_t)k * ncp + k] = 1.0;
 }
 
-// One Gauss-Jordan step (pivot k) of the in-place inversion, out of place between two buffers so that a step is ONE launch:
-// row k is divided by the pivot, every other row i loses A[i][k] times it, column k becomes the multipliers.
-static __global__ void gj_step_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int n, int ld, int k) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-  if (j >= n) return;
-  const double piv = 1.0 / Ain[(size_t)k * ld + k];
-  const double rkj = j == k ? piv : Ain[(size_t)k * ld + j] * piv;
-  double out;
-  if (i == k) out = rkj;
-  else {
-    const double f = Ain[(size_t)i * ld + k];
-    out = (j == k ? 0.0 : Ain[(size_t)i * ld + j]) - f * rkj;
+// Inverse of the Galerkin operator.  With the nodes numbered row by row Ac is BANDED (9-point coarse stencil: half-bandwidth
+// ncx + 1), so it is factored as a band (LU without pivoting: Ac is definite like L) and the dense inverse is obtained
+// column by column with band substitutions: O(nc^2 bw) instead of the O(nc^3) of a dense elimination.
+// band_lu_kernel: one block per operator set; the band is held as Lb[i][d] = L(i, i-bw+d) (d < bw, unit diagonal not stored)
+// and Ub[i][d] = U(i, i+d) (d <= bw), both [nc][bw+1] doubles in `band` (2 nc (bw+1) doubles per set).
+static __global__ void __launch_bounds__(1024) band_lu_kernel(const double* __restrict__ Ac, double* __restrict__ band, int nc, int ncp, int bw) {
+  extern __shared__ double wk[];                 // the active window: matrix rows k..k+bw, each as columns i-bw..i+bw (2 bw + 1 values),
+  const int W = 2 * bw + 1, R = bw + 1;          // matrix row i in window slot i % (bw + 1)
+  Ac += (size_t)blockIdx.x * ncp * ncp;
+  double* Lb = band + (size_t)blockIdx.x * 2 * nc * (bw + 1);
+  double* Ub = Lb + (size_t)nc * (bw + 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  auto load_row = [&](int i) {                   // (all threads) matrix row i -> its slot
+    for (int t = tid; t < W; t += nt) {
+      const int j = i - bw + t;
+      wk[(i % R) * W + t] = (i < nc && j >= 0 && j < nc) ? Ac[(size_t)i * ncp + j] : 0.0;
+    }
+  };
+  for (int i = 0; i <= bw; ++i) load_row(i);
+  __syncthreads();
+  for (int k = 0; k < nc; ++k) {
+    const double* pr = wk + (k % R) * W;         // pivot row k: U(k, k + t) at position bw + t
+    const double piv = pr[bw];
+    for (int t = tid; t <= bw; t += nt) Ub[(size_t)k * (bw + 1) + t] = pr[bw + t];
+    // eliminate column k from rows k+1..k+bw: row k+r has its column k at position bw - r, column k + c at bw - r + c
+    for (int t = tid; t < bw * (bw + 1); t += nt) {
+      const int r = 1 + t / (bw + 1), c = t % (bw + 1);
+      if (k + r < nc) {
+        double* row = wk + ((k + r) % R) * W;
+        const double l = row[bw - r] / piv;
+        if (c == 0) Lb[(size_t)(k + r) * (bw + 1) + (bw - r)] = l;            // L(k+r, k)
+        else row[bw - r + c] -= l * pr[bw + c];
+      }
+    }
+    __syncthreads();
+    load_row(k + bw + 1);                        // the slot of row k is free now
+    __syncthreads();
   }
-  Aout[(size_t)i * ld + j] = out;
+}
+// band_inverse_kernel: thread = one column j of the inverse of one operator set: forward substitution L y = e_j, back
+// substitution U x = y, the running vector kept in the output column itself (consecutive threads -> consecutive addresses).
+static __global__ void __launch_bounds__(128) band_inverse_kernel(const double* __restrict__ band, double* __restrict__ Ainv, int nc, int ncp, int bw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nc) return;
+  const double* Lb = band + (size_t)blockIdx.y * 2 * nc * (bw + 1);
+  const double* Ub = Lb + (size_t)nc * (bw + 1);
+  double* x = Ainv + (size_t)blockIdx.y * ncp * ncp + j;          // x(i) = x[i * ncp]
+  for (int i = 0; i < nc; ++i) {                                   // y(i) = e_j(i) - sum_{k = i-bw}^{i-1} L(i,k) y(k); y(i) = 0 for i < j
+    double t = i == j ? 1.0 : 0.0;
+    if (i > j) {
+      const int k0 = max(max(i - bw, 0), j);
+      for (int k = k0; k < i; ++k) t = fma(-Lb[(size_t)i * (bw + 1) + (k - i + bw)], x[(size_t)k * ncp], t);
+    }
+    x[(size_t)i * ncp] = t;
+  }
+  for (int i = nc - 1; i >= 0; --i) {                              // x(i) = (y(i) - sum_{k = i+1}^{i+bw} U(i,k) x(k)) / U(i,i)
+    double t = x[(size_t)i * ncp];
+    const int k1 = min(i + bw, nc - 1);
+    for (int k = i + 1; k <= k1; ++k) t = fma(-Ub[(size_t)i * (bw + 1) + (k - i)], x[(size_t)k * ncp], t);
+    x[(size_t)i * ncp] = t / Ub[(size_t)i * (bw + 1)];
+  }
 }
 
 // Rc[n][node] = P^T r from the per-tile moments written by sweep_line_kernel<.., TWO>: part[n][tile][kind 0..3][segment 0..7],
@@ -201,17 +251,26 @@ static __global__ void coarse_finish_kernel(const double* __restrict__ Ck, doubl
 
 // The same product for a handful of solves (the spectral probes run on 1 solve): one warp per coarse unknown i, lanes over k,
 // shuffle reduction (the DMMA kernel would walk its 128 k-steps with 4 warps: ~50 us of pure latency).
-static __global__ void __launch_bounds__(256) coarse_matvec_kernel(const double* __restrict__ Ainv, const double* __restrict__ Rc,
-                                                                   double* __restrict__ Cv, const int* __restrict__ done, double scale,
+static __global__ void __launch_bounds__(256) coarse_matvec_kernel(const double* __restrict__ Ainv, long long ainv_stride,
+                                                                   const double* __restrict__ Rc, double* __restrict__ Cv,
+                                                                   const int* __restrict__ done, double scale, const double* __restrict__ scale_ps,
                                                                    int nb, int nc, int ncp, int ncx, int px, int pzpx) {
+  // ainv_stride != 0: one coarse operator per solve (time series); scale_ps: per-solve factor (per-solve Chebyshev weight)
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, n = blockIdx.y;
   if (i >= nc || (done && done[n])) return;
-  const double* ar = Ainv + (size_t)i * ncp; const double* rc = Rc + (size_t)n * ncp;
+  const double* ar = Ainv + (size_t)n * ainv_stride + (size_t)i * ncp; const double* rc = Rc + (size_t)n * ncp;
   double t = 0.0;
   for (int k = lane; k < ncp; k += 32) t = fma(ar[k], rc[k], t);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  if (lane == 0) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * t;
+  if (lane == 0) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = (scale_ps ? scale_ps[n] : scale) * t;
+}
+// per-solve factor of the coarse correction, -omega_k(rho_n) gamma (one operator per solve: the sweep kernel computes the same
+// omega from the same rho)
+template <class T>
+__global__ void coarse_scale_kernel(const T* __restrict__ rho_ps, int cheb_k, double gamma, double* __restrict__ scale_ps, int nb) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nb) scale_ps[n] = -(double)(T)cheb_omega(cheb_k, (double)rho_ps[n]) * gamma;
 }
 
 // x += P Cv on the interior points (bilinear; the rim of Cv is zero, which is the Dirichlet condition of the correction).
