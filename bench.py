@@ -314,8 +314,18 @@ def run_ours(args):
     clocks = sampler.finish() if sampler else None
     ms_per_step = ms_total / args.steps
     value = total / (ms_per_step * 1e-3)
-    assert np.all((tab[:, 2] == 0) | (tab[:, 2] == 4)), "a solve hit max_iter or exploded: not converged"
+    # every rank's solves must have converged (err 0) or stopped on their round-off floor (err 4); sweep range over all ranks
+    ok = float(np.all((tab[:, 2] == 0) | (tab[:, 2] == 4)))
     n_floor = int((tab[:, 2] == 4).sum())
+    sw_min, sw_max = float(tab[:, 0].min()), float(tab[:, 0].max())
+    if world > 1:
+        t = torch.tensor([ok, -sw_min, sw_max, -float(n_floor)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = float(t[0].item()); sw_min = -float(t[1].item())
+        t = torch.tensor([sw_max, float(n_floor)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); sw_max = float(t[0].item())
+        t = torch.tensor([float(n_floor)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM); n_floor = int(t[0].item())
+    assert ok == 1.0, "a solve hit max_iter or exploded on some rank: not converged"
     # roofline of the dominant kernel: useful point-sweeps actually performed (per-solve sweep counts) x bytes
     interior = (NR - 2) * (NZ - 2)
     cheb = args.method.endswith("chebyshev"); line = args.method.startswith("line")
@@ -337,7 +347,7 @@ def run_ours(args):
                 "avg_launch_us": sweep_ms / max(sweep_launches, 1) * 1e3, "launches": sweep_launches,
                 "avg_sweep_us": sweep_ms / max(sweeps_done, 1) * 1e3, "sweeps": sweeps_done,
                 "algorithmic_bytes_per_point_sweep": b_alg, "kernel_share_of_step": sweep_ms / ms_total,
-                "sweeps_per_solve": [float(tab[:, 0].min()), float(tab[:, 0].max())],
+                "sweeps_per_solve": [sw_min, sw_max],
                 "mean_active_fraction_of_batch": float(tab[:, 0].sum()) * args.steps / max(sweeps_done * nloc, 1)}
     if probe_ms is not None:
         roofline["spectral_probe_share_of_step"] = probe_ms / ms_total

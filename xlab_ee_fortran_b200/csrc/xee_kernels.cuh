@@ -290,6 +290,8 @@ __global__ void __launch_bounds__(128) finalize_check_kernel(SolveState<T> st, c
     if (lcnt >= lost_rate) { ccnt -= 1; lcnt = 0; }
   }
   if (detect_explode && !(err_now == err_now && R::abs(err_now) <= R::huge())) { stop = true; errb |= XEE_ERR_EXPLODE; }
+  // (accelerated methods pass detect_explode = 1) a residual 10^6 above the best one seen is a divergent iteration too
+  if (detect_explode && stall_checks > 0 && err_now > st.best_err[n] * T(1e6)) { stop = true; errb |= XEE_ERR_EXPLODE; }
   if (stall_checks > 0 && !stop) {   // opt-in: the residual sits on its round-off floor above r1
     if (err_now < st.best_err[n] * T(0.999)) { st.best_err[n] = err_now; st.stall[n] = 0; }
     else if (++st.stall[n] >= stall_checks) { stop = true; errb |= XEE_ERR_STALLED; }

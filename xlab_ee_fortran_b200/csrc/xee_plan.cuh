@@ -811,6 +811,7 @@ struct Plan : PlanBase {
   int estimate_rho(cudaStream_t s);
   int estimate_rho_subsampled(cudaStream_t s);
   std::vector<double> lmin_ps;       // two-level: per-set smallest eigenvalue of M^-1 L (host copy, for the subsampled estimate)
+  std::vector<double> radius_ps;     // per-set spectral radius rho (rho_ps holds the focal distance the weights are computed from)
   // Make the Chebyshev parameters of this call available: explicit value, cached estimate, or a fresh estimate.
   int prepare_cheb(double rho_given, cudaStream_t s) {
     if (rho_given > 0 && !use_two) {   // (the two-level methods also need the step length: they always estimate)
@@ -1071,11 +1072,65 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     for (int n = 0; n < ns; ++n) rho[n] = std::max(tl_gamma * tl_lmax - 1.0, 1.0 - tl_gamma * lmin[n]);
     if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: two-level spectrum of M^-1 L: [%.4e, %.4f], gamma %.4f\n", tl_lmin, tl_lmax, tl_gamma);
   }
-  rho_ps = rho;
-  for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];
+  // ---- stage C (line methods): complex eigenvalues.  With a strongly varying B the operator is not symmetric and the
+  // iteration matrix of a LINE splitting can have a complex pair mu = +- i b (measured on the later snapshots of the time
+  // series: b = 0.09 at |rho| = 0.9995; the point splitting keeps a real spectrum).  Chebyshev weights for the real interval
+  // [-rho, rho] amplify such a mode by e^(asinh(b) - acosh(1/rho)) per sweep: divergence once b > sqrt(2 (1 - rho)).  The
+  // spectrum then lies in the ellipse with semi-axes (rho, b), for which the same recurrence with the FOCAL distance
+  // c = sqrt(rho^2 - b^2) in place of rho is the optimal choice (Manteuffel), convergence factor (rho + b) / (1 + sqrt(1 - c^2)).
+  // b is measured like rho in stage B: homogeneous problem, rough start vector, decay between sweeps p and 2p against the
+  // decay 1/T_k(1/c) that every mode inside the ellipse shows; repeated with the new c until the excess is gone.
+  std::vector<double> foci(rho);
+  radius_ps = rho;
+  if (use_line && env_int("XEE_RHO_ELLIPSE", 1)) {
+    const int pc = env_int("XEE_RHO_PROBE_C", 64), roundsC = 3;
+    uint32_t lcg = 12345u;
+    for (int j = 1; j < d.ny - 1; ++j)
+      for (int i = 1; i < d.nx - 1; ++i) { lcg = lcg * 1664525u + 1013904223u; h[(size_t)j * d.nx + i] = (T)((double)(lcg >> 8) / 8388608.0 - 1.0); }
+    std::vector<char> doneC(ns, 0);
+    for (int r = 0; r < roundsC && !rc; ++r) {
+      for (int n = 0; n < ns; ++n) rho_h[n] = (T)foci[n];
+      XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
+      for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+      XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+      if (use_two && two_reset(ns, s)) return 1;
+      parity = 0;
+      for (int k = 1; k <= 2 * pc && !rc; ++k) {
+        rc = sweep(MODE_CHEBYSHEV, k);
+        if (k == pc || k == 2 * pc) rc = rc || flush();
+        if (k == pc) rc = rc || norms(parity ? e1 : e0, nA);
+        if (k == 2 * pc) rc = rc || norms(parity ? e1 : e0, nB);
+      }
+      if (rc) break;
+      bool all = true;
+      for (int n = 0; n < ns; ++n) {
+        if (doneC[n]) continue;
+        if (!(nA[n] > 1e-280) || !(nB[n] > 1e-280) || !std::isfinite(nB[n])) { doneC[n] = 1; continue; }
+        const double c = (double)rho_h[n], o = std::acosh(1.0 / c);
+        const double excess = std::log(nB[n] / nA[n]) - (lncosh((double)pc * o) - lncosh(2.0 * pc * o));   // vs the decay of the modes inside
+        if (excess < 0.7) { doneC[n] = 1; continue; }                 // within the scatter of a sum over many modes
+        // the dominant outside mode multiplies its amplitude by e^(asinh(y)) per sweep, y = distance from the focal segment in
+        // units of c along the imaginary axis; the ellipse through it keeps the real semi-axis rho
+        const double y = std::sinh(excess / pc);
+        const double bsq = (c * y) * (c * y) + (rho[n] * rho[n] - c * c);   // imaginary semi-axis of the new ellipse (squared)
+        const double c2 = rho[n] * rho[n] - 1.21 * bsq;                       // 10 % margin on b
+        foci[n] = std::sqrt(std::max(c2, 1e-4));
+        all = false;
+      }
+      if (all) break;
+    }
+    if (rc) return 1;
+    if (env_int("XEE_TRACE", 0)) {
+      double worst = 0.0;
+      for (int n = 0; n < ns; ++n) worst = std::max(worst, std::sqrt(std::max(rho[n] * rho[n] - foci[n] * foci[n], 0.0)));
+      fprintf(stderr, "xee: largest imaginary semi-axis of the iteration spectrum: %.4f\n", worst);
+    }
+  }
+  rho_ps = foci;   // what the Chebyshev weights are computed from
+  for (int n = 0; n < ns; ++n) rho_h[n] = (T)foci[n];
   XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
   XEE_CHECK(cudaStreamSynchronize(s));
-  cheb_rho = rho[0];
+  cheb_rho = foci[0];
   if (env_int("XEE_TRACE", 0)) fprintf(stderr, "xee: Jacobi spectral radius estimate rho[0] = 1 - %.4e (%d operator set%s)\n", 1.0 - rho[0], ns, ns > 1 ? "s" : "");
   return 0;
 }
@@ -1103,15 +1158,20 @@ int Plan<T>::estimate_rho_subsampled(cudaStream_t s) {
   if (sub.estimate_rho(sub.own_stream)) return 1;
   // the interpolated quantity at the sampled sets
   std::vector<double> v(nq);
-  for (int q = 0; q < nq; ++q) v[q] = use_two ? sub.lmin_ps[q] : 1.0 - sub.rho_ps[q];
+  std::vector<double> bq(nq);       // imaginary semi-axis of the iteration spectrum at the sampled sets (stage C)
+  for (int q = 0; q < nq; ++q) {
+    v[q] = use_two ? sub.lmin_ps[q] : 1.0 - sub.radius_ps[q];
+    bq[q] = std::sqrt(std::max(sub.radius_ps[q] * sub.radius_ps[q] - sub.rho_ps[q] * sub.rho_ps[q], 0.0));
+  }
   for (int q = 0; q < nq; ++q)
     if (!(v[q] > 0.0)) return fail("xee: subsampled spectral estimate: non-positive gap");
-  std::vector<double> rho(nsets), lmin(nsets);
+  std::vector<double> rho(nsets), lmin(nsets), bim(nsets);
   double mean = 0.0;
   for (int n = 0, q = 0; n < nsets; ++n) {
     while (q + 1 < nq - 1 && idx[q + 1] <= n) ++q;
     const double t = idx[q + 1] > idx[q] ? (double)(n - idx[q]) / (idx[q + 1] - idx[q]) : 0.0;
     lmin[n] = std::exp((1.0 - t) * std::log(v[q]) + t * std::log(v[q + 1]));
+    bim[n] = std::max(bq[q], bq[q + 1]);        // the larger neighbour: an over-estimate costs sweeps, an under-estimate convergence
     mean += lmin[n] / nsets;
   }
   if (use_two) {
@@ -1122,6 +1182,8 @@ int Plan<T>::estimate_rho_subsampled(cudaStream_t s) {
   } else {
     for (int n = 0; n < nsets; ++n) rho[n] = 1.0 - lmin[n];
   }
+  radius_ps = rho;
+  for (int n = 0; n < nsets; ++n) rho[n] = std::sqrt(std::max(rho[n] * rho[n] - bim[n] * bim[n], 1e-4));   // focal distances
   if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * nsets));
   std::vector<T> rho_h(nsets);
   for (int n = 0; n < nsets; ++n) rho_h[n] = (T)rho[n];
