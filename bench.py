@@ -339,7 +339,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     k = workload_constants()
     # dram bytes of ONE full-batch launch of this variant from its ncu --set full capture (profiles/), None if not captured
-    traffic = None if series else k.get(f"sweep_kernel_dram_bytes_per_launch_v{variant}", k.get("sweep_kernel_dram_bytes_per_launch") if variant == 2 else None)
+    tkey = f"sweep_kernel_dram_bytes_per_launch_v{variant}" + ("_two_level" if args.method.startswith("line2") else "")
+    traffic = None if series else k.get(tkey, k.get("sweep_kernel_dram_bytes_per_launch") if variant == 2 else None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "kernel": KERNEL_NAMES.get(variant, "sweep") + " (K3/K4)",

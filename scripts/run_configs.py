@@ -13,7 +13,7 @@ ACC = "chebyshev"      # accelerated method of configs 2 and 3: --method line_ch
 argv = sys.argv[1:]
 if "--method" in argv:
     k = argv.index("--method"); ACC = argv[k + 1]; del argv[k:k + 2]
-CS = 25 if ACC.startswith("line") else 100
+CS = 10 if ACC.startswith("line2") else 25 if ACC.startswith("line") else 100
 which = [int(a) for a in argv] or [2, 3, 5]
 out = {}
 Lr, Lz = (0.0, 1.0e6), (0.0, 1.5e4)
