@@ -319,9 +319,9 @@ def run_ours(args):
     n_floor = int((tab[:, 2] == 4).sum())
     sw_min, sw_max = float(tab[:, 0].min()), float(tab[:, 0].max())
     if world > 1:
-        t = torch.tensor([ok, -sw_min, sw_max, -float(n_floor)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = float(t[0].item()); sw_min = -float(t[1].item())
-        t = torch.tensor([sw_max, float(n_floor)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ok, sw_min], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = float(t[0].item()); sw_min = float(t[1].item())
+        t = torch.tensor([sw_max], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX); sw_max = float(t[0].item())
         t = torch.tensor([float(n_floor)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM); n_floor = int(t[0].item())
