@@ -187,3 +187,24 @@ def test_efficiency_map_with_the_two_level_method():
     for k in range(len(heat)):
         assert rel_l2(psis["line2_chebyshev"][k], psis["line_chebyshev"][k]) < 1e-8
     assert t1[:, 0].max() <= 400
+
+
+def test_drop_in_entry_with_the_two_level_method(monkeypatch):
+    """solve_elliptic (the Fortran-facing signature) with XEE_METHOD=line2_chebyshev XEE_ARITH=fast: reference case test1
+    (200x200, fp64) converged to a tight r1 agrees with the reference iteration run to the same tolerance."""
+    torch, X, O = _mods()
+    from tests.util import ref_test1_inputs
+    A, B, C, bc = ref_test1_inputs()
+    d = O.Domain((0.0, 1.0), (0.0, 1.0), 200, 200, 0, 0)
+    a, b, c = O.build_abc(A.astype(np.float64), B.astype(np.float64), C.astype(np.float64), d)
+    g = O.geometry(d, np.float64)
+    coe, _ = O.cal_coe(a, b, c, g["dr"], g["dz"], 200, 200)
+    f = -B.astype(np.float64)                       # DYNAMIC_EFFICIENCY: f = -B_in (initialize-variables.f90:38-42)
+    r1 = 1e-10 * float(np.sqrt((f[1:-1, 1:-1] ** 2).mean()))
+    ref = O.solve_elliptic(2000000, 100, 2, 5, r1, 0.0, 1.0, bc.astype(np.float64), coe, f)
+    assert ref["err"] == 0
+    monkeypatch.setenv("XEE_METHOD", "line2_chebyshev"); monkeypatch.setenv("XEE_ARITH", "fast")
+    dat = bc.astype(np.float64).copy(); wk = np.zeros_like(dat)
+    it, r1o, r2o, err = X.solve_elliptic(2000000, 10, 2, 5, r1, 0.0, 1.0, dat, coe, f, wk, 200, 200)
+    assert err == 0 and r1o < r1 and it * 50 < ref["max_iter"], (it, ref["max_iter"])
+    assert rel_l2(dat, ref["dat"]) < 1e-8

@@ -102,7 +102,8 @@ PlanBase* new_plan_or_die(int dtype, int nx, int ny, int nbatch, int shared) {
   d.arith = (ar && !strcmp(ar, "fast")) ? XEE_ARITH_FAST : XEE_ARITH_STRICT;
   const char* me = getenv("XEE_METHOD");
   d.method = !me ? XEE_METHOD_JACOBI : !strcmp(me, "chebyshev") ? XEE_METHOD_CHEBYSHEV : !strcmp(me, "line_jacobi") ? XEE_METHOD_LINE_JACOBI
-             : !strcmp(me, "line_chebyshev") ? XEE_METHOD_LINE_CHEBYSHEV : XEE_METHOD_JACOBI;
+             : !strcmp(me, "line_chebyshev") ? XEE_METHOD_LINE_CHEBYSHEV : !strcmp(me, "line2_jacobi") ? XEE_METHOD_LINE2_JACOBI
+             : !strcmp(me, "line2_chebyshev") ? XEE_METHOD_LINE2_CHEBYSHEV : XEE_METHOD_JACOBI;
   PlanBase* p = nullptr;
   if (make_plan(&d, &p)) die("plan create");
   return p;
