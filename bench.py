@@ -26,6 +26,7 @@ snapshots (strong scaling: `--total 4096` is BASELINE config 4 as written at eve
 `e2e`    : the same metric through the host-facing call (HOST A,B,C + heating table in, efficiency
            table out; H2D/D2H and operator assembly inside the timed region).
 `roofline`: dominant kernel = the sweep kernel; achieved = algorithmic bytes / CUDA-event time.
+`roofline_streaming_kernel`: the same for the one-level variant of the kernel (pure HBM streaming), one extra pass (N=1).
 `cpu_baseline`: the oracle's literal restatement of the reference algorithm on the host cores, three variants
            (`ref_O3` = reference loop order at -O3, `ref_O0` = the same at -O0 like make-diagnosis.sh:10-11, `fair` = fused,
            contiguous loop order), each a bounded sample of Jacobi sweeps; solves/s EXTRAPOLATED linearly to the Jacobi sweep
@@ -365,6 +366,25 @@ def run_ours(args):
         lfl = {"gpu_point_sweeps_per_s": nloc * jsw * interior / (jms * 1e-3), "gpu_sweeps_timed": int(jsw), "gpu_kernel_variant": mj.kernel_info()[0],
                "gpu_arithmetic": "strict (every operation separately rounded, reference order: iterates bit-identical to the oracle)"}
         mj.close()
+    # ------------------------------------------------------------------ the streaming kernel on its own
+    # The default (two-level) sweep kernel is instruction-bound by design (it also restricts the residual and adds the coarse
+    # correction on the fly); the ONE-level kernel is the pure HBM-streaming variant of the same code.  One untimed + one timed
+    # pass of the same workload with it, so that the driver's record carries its roofline next to the headline's.
+    streaming = None
+    if rank == 0 and world == 1 and not series and args.method.startswith("line2") and not args.no_streaming:
+        ms1 = EfficiencyMap(A, B, C, LR, LZ, nloc, "f64", arith=args.arith, method="line_chebyshev", r1_rel=R1_REL, device=local)
+        p1 = X.SolveParams(max_iter=args.max_iter, check_step=25, converge_time=2, r1=1.0, r2=0.0, alpha=1.0, sync_every=2, stall_checks=10)
+        ms1.run_dev(heat_t, table_t, p1); ms1.sweep_kernel_stats(reset=True)
+        t0 = time.perf_counter(); ms1.run_dev(heat_t, table_t, p1); torch.cuda.synchronize(); dt1 = time.perf_counter() - t0
+        sms, ssw = ms1.sweep_kernel_stats(); t1 = table_t.cpu().numpy()
+        b1 = 8.0 * (4 + 13.0 / nloc)
+        a1 = float(t1[:, 0].sum()) * interior * b1 / (sms * 1e-3) / 1e9
+        streaming = {"kernel": "sweep_line_kernel (v5, one-level: method line_chebyshev)", "bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s",
+                     "frac": a1 / peak, "traffic": k.get("sweep_kernel_dram_bytes_per_launch_v5"), "avg_launch_us": sms / max(ssw, 1) * 1e3,
+                     "launches": int(ssw), "sweeps_per_solve": [float(t1[:, 0].min()), float(t1[:, 0].max())],
+                     "mean_active_fraction_of_batch": float(t1[:, 0].sum()) / max(ssw * nloc, 1), "solves_per_s": nloc / dt1,
+                     "algorithmic_bytes_per_point_sweep": b1}
+        ms1.close()
     if not series:
         del heat_t, table_t
     # ------------------------------------------------------------------ e2e leg (host buffers, whole call)
@@ -441,7 +461,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total > 0 else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, f"{args.method} ({args.arith} arithmetic)"),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "roofline_streaming_kernel": streaming, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 # the reference arm (--impl reference) runs the reference's plain Jacobi, extrapolated: not the same iteration
                 "same_config": False,
                 "same_config_note": "GPU arm: Chebyshev-accelerated (two-level) block-line relaxation to the same residual tolerance; reference arm: "
@@ -477,6 +497,7 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=4000, help="Jacobi sweeps per solve in one CPU sample")
     ap.add_argument("--lfl-sweeps", type=int, default=300, help="GPU STRICT Jacobi sweeps timed for like_for_like")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the extra one-level pass that reports the streaming kernel's roofline")
     args = ap.parse_args()
     if args.method is None:
         args.method = "line_chebyshev" if args.workload == "series" else "line2_chebyshev"

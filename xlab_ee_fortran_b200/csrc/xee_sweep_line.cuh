@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
   constexpr int RES_OFS = AFTER + C::FAC_BYTES + C::NOUT * C::OUT_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NSTAGE];
-  __shared__ double red[NT / 32];
+  __shared__ double red[2][NT / 32];          // per-warp sums of r^2 (CHECK), double-buffered by iteration parity
   __shared__ uint32_t sdone[kDoneWords];   // stop flags of the batch as a bit mask: no global load per (tile, solve)
 
   const int tid = threadIdx.x;
@@ -586,6 +586,11 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
         fence_proxy_async_smem();
         if (tid == 0) tma_store_wait_read0();
       }
+      if (CHECK) {   // per-warp sum of r^2 into this iteration's buffer BEFORE the barrier: no barrier of its own
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, q);
+        if ((tid & 31) == 0) red[it & 1u][tid >> 5] = rr;
+      }
       cta_bar_sync();                           // every thread is done with the stage (and has staged its results)
       if (tid == 0) {
         issue_next();                           // ... refill it, NSTAGE items ahead
@@ -622,17 +627,10 @@ __global__ void __launch_bounds__(ln::NT, ln::CTAS_PER_SM)
             if (gi + e < a.nx) o[e] = out[e];
         }
       }
-      if (CHECK) {
-#pragma unroll
-        for (int q = 16; q > 0; q >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, q);
-        if ((tid & 31) == 0) red[tid >> 5] = rr;
-        cta_bar_sync();
-        if (tid == 0) {
-          double t = 0.0;
-          for (int q = 0; q < NT / 32; ++q) t += red[q];
-          a.partial[(size_t)n * ntiles + tile] = t;
-        }
-        cta_bar_sync();
+      if (CHECK && tid == 0) {   // fixed order: deterministic.  (The buffer is rewritten two iterations on, after a barrier this thread has passed.)
+        double t = 0.0;
+        for (int q = 0; q < NT / 32; ++q) t += red[it & 1u][q];
+        a.partial[(size_t)n * ntiles + tile] = t;
       }
       ++it;
     }
