@@ -1,3 +1,5 @@
+"""Residual against sweeps for a few snapshots of the series and three methods (fixed max_iter runs).
+   python scripts/diagnostics/series_diag.py <first snapshot> <count>"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np

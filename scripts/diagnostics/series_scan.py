@@ -1,3 +1,6 @@
+"""Scans shards of the 1024-snapshot series (BASELINE config 5) on one GPU: sweeps, error flags and time per shard and method.
+   python scripts/diagnostics/series_scan.py 0 640 896      (first snapshot of every 128-snapshot shard to scan)
+This is how the non-converging shard of the first 8-GPU run was found (stage C)."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
