@@ -489,7 +489,7 @@ def main():
                     help="default: line2_chebyshev for the map workload, line_chebyshev for the series (one operator per solve)")
     ap.add_argument("--check-step", type=int, default=0,
                     help="sweeps between residual checks (solve_elliptic's check_step); 0 = 100 for the point methods, 25 for the "
-                         "line methods, which need ~4x fewer sweeps, 10 for the two-level method (a solve stops at the 2nd consecutive "
+                         "line methods, which need ~4x fewer sweeps, 5 for the two-level method (a solve stops at the 2nd consecutive "
                          "check below r1)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--max-iter", type=int, default=2000000)
@@ -502,7 +502,7 @@ def main():
     if args.method is None:
         args.method = "line_chebyshev" if args.workload == "series" else "line2_chebyshev"
     if args.check_step <= 0:
-        args.check_step = 10 if args.method.startswith("line2") else 25 if args.method.startswith("line") else 100
+        args.check_step = 5 if args.method.startswith("line2") else 25 if args.method.startswith("line") else 100
     args.per_gpu = args.nsnap if args.workload == "series" else args.nheat
     if args.total > 0:
         args.per_gpu = (args.total + max(args.gpus, 1) - 1) // max(args.gpus, 1)

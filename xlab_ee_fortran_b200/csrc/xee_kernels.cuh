@@ -220,18 +220,20 @@ __global__ void __launch_bounds__(kDirBX* kDirBY) sweep_direct_kernel(const Swee
   }
 }
 
-// D-weighted norm per solve, sqrt(sum |coe5| x^2), for the spectral-radius probe (one block per solve).
+// D-weighted norm per solve, sum |coe5| x^2, for the spectral-radius probes: kWnormParts blocks per solve write partial sums
+// (a single block per solve took 150 us for one 512x256 field: pure latency); the host adds them in a fixed order.
+constexpr int kWnormParts = 32;
 template <class T>
 __global__ void __launch_bounds__(256) wnorm_kernel(const T* __restrict__ x, const T* __restrict__ coe,
                                                     long long coe_set_stride, long long nn, double* __restrict__ out) {
   __shared__ double red[32];
-  const int n = blockIdx.x;
+  const int n = blockIdx.y, part = blockIdx.x;
   const T* xp = x + (size_t)n * nn;
   const T* w = coe + (size_t)n * coe_set_stride + 4 * nn;
   double s = 0;
-  for (long long q = threadIdx.x; q < nn; q += 256) s += fabs((double)w[q]) * (double)xp[q] * (double)xp[q];
+  for (long long q = (long long)part * 256 + threadIdx.x; q < nn; q += 256LL * kWnormParts) s += fabs((double)w[q]) * (double)xp[q] * (double)xp[q];
   const double t = block_sum(s, red, threadIdx.x, 8);
-  if (threadIdx.x == 0) out[n] = sqrt(t);
+  if (threadIdx.x == 0) out[(size_t)n * kWnormParts + part] = t;
 }
 
 // Per-solve control state of solve_elliptic (elliptic_tools.f90:160-164, 201-233).

@@ -924,7 +924,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     ~Restore() { p->d.nbatch = nb; p->gz = gz; p->spb = spb; pool_free(*e0); pool_free(*e1); pool_free(*zf); pool_free(*nrm); }
   } restore{this, d.nbatch, gz, spb, &e0, &e1, &zf, &nrm_d};
   XEE_CHECK(pool_alloc(&e0, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&e1, sizeof(T) * nn * ns));
-  XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&nrm_d, sizeof(double) * ns));
+  XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&nrm_d, sizeof(double) * ns * kWnormParts));
   if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * ns));
   XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn * ns, s));
   std::vector<T> h(nn, T(0));
@@ -937,11 +937,17 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   d.nbatch = ns; spb = 1; gz = ns;
   std::vector<double> nA(ns), nB(ns), rho(ns, 0.0);
   std::vector<T> rho_h(ns);
+  std::vector<double> nrm_h((size_t)ns * kWnormParts);
   auto norms = [&](const T* x, std::vector<double>& out) -> int {
-    wnorm_kernel<T><<<ns, 256, 0, s>>>(x, coe, d.shared_coe ? 0 : (long long)kPlanes * nn, (long long)nn, nrm_d);
+    wnorm_kernel<T><<<dim3(kWnormParts, ns), 256, 0, s>>>(x, coe, d.shared_coe ? 0 : (long long)kPlanes * nn, (long long)nn, nrm_d);
     XEE_LAUNCH_OK();
-    XEE_CHECK(cudaMemcpyAsync(out.data(), nrm_d, sizeof(double) * ns, cudaMemcpyDeviceToHost, s));
+    XEE_CHECK(cudaMemcpyAsync(nrm_h.data(), nrm_d, sizeof(double) * ns * kWnormParts, cudaMemcpyDeviceToHost, s));
     XEE_CHECK(cudaStreamSynchronize(s));
+    for (int n = 0; n < ns; ++n) {
+      double t = 0.0;
+      for (int q = 0; q < kWnormParts; ++q) t += nrm_h[(size_t)n * kWnormParts + q];
+      out[n] = std::sqrt(t);
+    }
     return 0;
   };
   int rc = 0, parity = 0;   // current iterate lives in (parity ? e1 : e0)
