@@ -13,7 +13,7 @@ built on the device, all solves to tolerance, energy integrals, efficiency table
 Method (`--method`, default line2_chebyshev): Chebyshev-accelerated TWO-LEVEL block-line relaxation (v5 kernel: 32-point radial
 blocks solved inside the sweep, plus a Galerkin coarse-grid correction on a 16 x 16-spaced bilinear space whose prolongation
 is fused into the sweep kernel; same residual, tolerance and stop rule as solve_elliptic); `line_chebyshev` = the one-level
-block-line method (the pure streaming kernel, last round's default; series workload default); `chebyshev` = accelerated point
+block-line method (the pure streaming kernel, last round's default); `chebyshev` = accelerated point
 Jacobi on the temporally blocked kernel (v4); `jacobi` = the reference iteration.  Results of all four agree within the
 north_star tolerances (tests/test_gpu_map.py, tests/test_gpu_line.py, tests/test_gpu_twolevel.py).
 
@@ -486,7 +486,7 @@ def main():
     ap.add_argument("--nsnap", type=int, default=128, help="series: snapshots (independent solves, one operator each) per GPU")
     ap.add_argument("--total", type=int, default=0, help="fix the TOTAL number of locations / snapshots (strong scaling); 0 = per-GPU count x GPUs")
     ap.add_argument("--method", default=None, choices=["chebyshev", "jacobi", "line_chebyshev", "line_jacobi", "line2_chebyshev"],
-                    help="default: line2_chebyshev for the map workload, line_chebyshev for the series (one operator per solve)")
+                    help="default: line2_chebyshev (two-level block-line Chebyshev), for both workloads")
     ap.add_argument("--check-step", type=int, default=0,
                     help="sweeps between residual checks (solve_elliptic's check_step); 0 = 100 for the point methods, 25 for the "
                          "line methods, which need ~4x fewer sweeps, 5 for the two-level method (a solve stops at the 2nd consecutive "
@@ -500,7 +500,7 @@ def main():
     ap.add_argument("--no-streaming", action="store_true", help="skip the extra one-level pass that reports the streaming kernel's roofline")
     args = ap.parse_args()
     if args.method is None:
-        args.method = "line_chebyshev" if args.workload == "series" else "line2_chebyshev"
+        args.method = "line2_chebyshev"
     if args.check_step <= 0:
         args.check_step = 5 if args.method.startswith("line2") else 25 if args.method.startswith("line") else 100
     args.per_gpu = args.nsnap if args.workload == "series" else args.nheat
