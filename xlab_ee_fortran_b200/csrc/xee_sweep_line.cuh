@@ -30,12 +30,16 @@
 //   * TWO persistent CTAs of 128 threads per SM (255 registers per thread: the register file is full), tiles of
 //     64 x 16 points, a 2-stage TMA ring per CTA (80 KB of shared memory each), one named barrier per (tile, solve) to
 //     hand the stage back; while one CTA reloads the operator of its next work unit or waits at its barrier the other
-//     one computes.  Results go to global memory as 128-bit stores;
+//     one computes.  Results are staged in shared memory (128-bit stores) and leave with one 4-D TMA store per
+//     (tile, solve) (tensor map = column in tile, tile column, row, solve: the pad columns of the last tile are dropped by
+//     the bounds check); a.tstore == 0 keeps the 128-bit global stores of round 1 (shapes the map cannot describe);
 //   * the operator and the factors are repacked once per operator in tile/thread order (line_pack_kernel), so the
 //     per-unit reload of a thread's constants is fully coalesced 128-bit loads (2-3 us per unit instead of 10).
-// Measured on B200 (512 solves, 512x256, fp64, Chebyshev): 377 us per sweep = 5.66 TB/s algorithmic (87 % of the measured
-// copy peak) with a shared operator; 6.1 TB/s of 136 B/point with one operator per solve (one CTA per SM on 64 x 32 tiles
-// with a 3-stage ring, XEE_LINE_TH=32 XEE_LINE_NSTAGE=3: 391 us and 4.4 TB/s).
+// TWO = true is the two-level variant (xee_twolevel.cuh): the iterate is stored as (field y, coarse vector c) with
+// psi = y + P c; the 3 x 8 coarse patch of a tile arrives with its stage, the correction is added to the values as they are
+// read, and the restriction moments of the new residual leave as 32 doubles per (tile, solve).
+// Measured on B200 (512 solves, 512x256, fp64, Chebyshev, ncu, profiles/r02_*): one level 355 us per sweep = 6.05 TB/s
+// algorithmic (97 % of the measured copy peak) with a shared operator; two-level 585 us (instruction/latency bound).
 #pragma once
 #include <cuda.h>
 
