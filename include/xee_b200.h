@@ -71,7 +71,8 @@ void xee_solve_elliptic_f64(int* max_iter, const int* check_step, const int* con
  * src/old-diagnose/xtt-lib/elliptic_tools.f90:93-300, called nine times by src/old-diagnose/diagnose.f90:449-714.
  * strategy 1: stop when the RMS residual < strategy_r at a check (every 100 sweeps); strategy 2: stop when the relative
  * change of the residual stays < strategy_r for 10 checks (hysteresis 5).  On return strategy = sweeps used,
- * strategy_r = last residual.  Strategies 3/4 (max-abs residual) are not provided: err = 2^8 and no work is done.
+ * strategy_r = last residual.  Strategies 3 / 4: the same two rules with the residual measured as maxval(abs(to_dat)) (:203-204) -
+ * the largest |L psi - f| of the interior joined with the largest |boundary value| of dat; point methods only.
  * As in the legacy code, max_iter is only honoured on check sweeps (multiples of 100). */
 void xee_solve_elliptic_old_f32(const int* max_iter, int* strategy, float* strategy_r, const float* alpha, float* dat,
                                 const float* coe, const float* f, float* workspace, const int* nx, const int* ny,

@@ -17,6 +17,52 @@ def old_solve(strategy, strategy_r, max_iter, alpha, dat, coe, f):
     return r["dat"], r["max_iter"], r["r1"]
 
 
+def old_solve_loop(strategy, strategy_r, max_iter, alpha, dat, coe, f):
+    """The legacy loop itself (old-diagnose/xtt-lib/elliptic_tools.f90:168-300) for strategies 1..4, in the working precision
+    of `dat`: strategies 3 / 4 measure err_now = maxval(abs(to_dat)) (:203-204) over the WHOLE array - residual in the interior,
+    Dirichlet values on the rim.  Returns dict(dat, strategy (sweeps used, or the input when the loop falls through),
+    strategy_r, err)."""
+    dt = dat.dtype.type
+    sr = dt(strategy_r); alpha = dt(alpha)
+    huge = np.finfo(dat.dtype).max
+    err_before = huge; err_now = dt(0); err = 0
+    conv = 0; lose = 0
+    fr = dat.copy(); to = dat.copy()                                    # :160-165  workspace = dat
+    negc5 = -coe[1:-1, 1:-1, 4]; fint = f[1:-1, 1:-1]
+    out_strategy, out_r = strategy, sr
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for cnt in range(1, max_iter + 1):
+            flag = cnt % 100 == 0                                       # :170-174
+            fr, to = to, fr
+            res = N.apply_interior(fr, coe) - fint                      # :180-181
+            stop = False
+            if flag:
+                if strategy in (1, 2):
+                    err_now = N.rms_residual_sequential(res)            # :193-201
+                else:
+                    whole = to.copy(); whole[1:-1, 1:-1] = res
+                    err_now = np.abs(whole).max()                       # :203-204
+                ratio = (err_before - err_now) / err_before             # :208
+            to[1:-1, 1:-1] = fr[1:-1, 1:-1] + alpha * res / negc5       # :241
+            if flag:
+                if strategy in (1, 3):
+                    if err_now < sr: stop = True                        # :246-249
+                else:
+                    if err_before == 0: stop = True
+                    elif abs(ratio) < sr:
+                        conv += 1; lose = 0
+                        if conv >= 10: stop = True
+                    elif conv > 0:
+                        lose += 1
+                        if lose >= 5: conv -= 1; lose = 0
+                    err_before = err_now                                # :279
+                if cnt == max_iter: stop = True; err |= 1               # :281-287
+                if stop:
+                    out_strategy, out_r = cnt, err_now                  # :292
+                    break
+    return dict(dat=to, strategy=out_strategy, strategy_r=float(out_r), err=err)
+
+
 def exchange_conversion(rpsi, rchi, rhoC, g):
     """cal_exchange_conversion (old-diagnose/diagnose.f90:1143-1174): the top/bottom boundary exchange term
     (rhoC/rho) (psi d(chi)/dz - chi d(psi)/dz) / r^2 at the mid-points of the first and last row, and its integral

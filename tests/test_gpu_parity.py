@@ -514,3 +514,47 @@ def test_pin_checker_accepts_the_rehosted_driver_output(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "pin_check.py"), str(tmp_path / "sweeps1000"), str(tmp_path / "stop")],
                        capture_output=True, text=True)
     assert r.returncode == 0 and "PINNED" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("strategy,sr,zero_rim", [(3, 1e-2, True), (3, 1e-3, True), (4, 0.3, True), (4, 0.05, False), (3, 1e-3, False),
+                                                 (1, 1e-3, False), (2, 0.3, True)])
+def test_legacy_solve_elliptic_strategies(dt, strategy, sr, zero_rim):
+    """Legacy strategies 1..4 (src/old-diagnose/xtt-lib/elliptic_tools.f90:190-204, :246-279) through the drop-in against a
+    restatement of the legacy loop: 3 / 4 measure maxval(abs(to_dat)) - the largest interior residual joined with the largest
+    Dirichlet value on the rim (so with a non-zero rim strategy 3 never converges and strategy 4 sees a constant).  Sweeps used,
+    returned residual, error code and field bit for bit."""
+    import ctypes as C
+    from tests import legacy_oracle as L
+    torch, X, O = _mods()
+    nx, ny = 48, 36
+    a, b, c, f, x0 = _rand_case(nx, ny, dt, seed=31)
+    if zero_rim:
+        x0[0] = 0; x0[-1] = 0; x0[:, 0] = 0; x0[:, -1] = 0
+    coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    ref = L.old_solve_loop(strategy, sr, 3000, 0.9, x0, coe, f)
+    dat = x0.copy(); wk = np.zeros_like(dat)
+    ct = C.c_double if dt is np.float64 else C.c_float
+    st = C.c_int(strategy); srv = ct(sr); err = C.c_int(-7)
+    p = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    fn = X._lib.lib().xee_solve_elliptic_old_f64 if dt is np.float64 else X._lib.lib().xee_solve_elliptic_old_f32
+    fn(C.byref(C.c_int(3000)), C.byref(st), C.byref(srv), C.byref(ct(0.9)), p(dat), p(coe), p(f), p(wk),
+       C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), C.byref(err), C.byref(C.c_int(0)))
+    assert st.value == ref["strategy"] and err.value == ref["err"]
+    if strategy >= 3:      # a maximum is exact in any order
+        assert dt(srv.value) == dt(ref["strategy_r"])
+    else:                  # the RMS is a sum: sequential in the reference, a fixed tree on the device
+        assert srv.value == pytest.approx(ref["strategy_r"], rel=1e-12 if dt is np.float64 else 2e-5)
+    assert np.array_equal(dat, ref["dat"])
+
+
+def test_legacy_solve_elliptic_rejects_unknown_strategy():
+    import ctypes as C
+    torch, X, O = _mods()
+    nx, ny = 16, 12
+    z = np.zeros((ny, nx)); coe = np.zeros((ny, nx, 9)); wk = np.zeros_like(z)
+    st = C.c_int(5); sr = C.c_double(1e-3); err = C.c_int(0)
+    p = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    X._lib.lib().xee_solve_elliptic_old_f64(C.byref(C.c_int(100)), C.byref(st), C.byref(sr), C.byref(C.c_double(1.0)), p(z), p(coe), p(z), p(wk),
+                                            C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), C.byref(err), C.byref(C.c_int(0)))
+    assert err.value == 1 << 8 and st.value == 5

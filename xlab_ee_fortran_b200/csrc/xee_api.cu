@@ -191,12 +191,15 @@ void solve_elliptic_impl(int* max_iter, const int* check_step, const int* conver
 }
 
 // Legacy 12-argument solve_elliptic (src/old-diagnose/xtt-lib/elliptic_tools.f90:93-300) on top of the current solver:
-//   strategy 1 = r1 only, converge_time 1;   strategy 2 = r2 only, converge_time 10, lost_rate 5.
+//   strategy 1 = r1 only, converge_time 1;   strategy 2 = r2 only, converge_time 10, lost_rate 5;
+//   strategies 3 / 4 = the same two rules on err_now = maxval(abs(to_dat)) (:203-204): the largest |residual| of the interior
+//   joined with the largest |value| on the rim of the array (to_dat's rim holds the Dirichlet values of dat).
 template <class T>
 void solve_elliptic_old_impl(const int* max_iter, int* strategy, T* strategy_r, const T* alpha, T* dat, const T* coe,
                              const T* f, T* workspace, const int* nx, const int* ny, int* err, const int* debug) {
   *err = 0;
-  if (*strategy != 1 && *strategy != 2) { *err = 1 << 8; fprintf(stderr, "xee_b200: legacy strategy %d (max-abs residual) is not provided\n", *strategy); return; }
+  if (*strategy < 1 || *strategy > 4) { *err = 1 << 8; fprintf(stderr, "xee_b200: legacy strategy %d does not exist (1..4)\n", *strategy); return; }
+  const bool maxnorm = *strategy >= 3, absolute = (*strategy & 1) != 0;
   // The legacy loop `do cnt = 1, max_iter` (:168) runs ALL max_iter sweeps; the stop tests and `cnt == max_iter` are evaluated
   // on check sweeps only (every 100th, :293-305).  A run that never stops on a check and whose max_iter is not a multiple of
   // 100 therefore falls out of the loop with err = 0, strategy / strategy_r untouched and judge_error not called.
@@ -204,10 +207,18 @@ void solve_elliptic_old_impl(const int* max_iter, int* strategy, T* strategy_r, 
   if (mi <= 0) { memcpy(workspace, dat, sizeof(T) * (size_t)*nx * *ny); return; }
   PlanBase* p = new_plan_or_die(dtype_of<T>(), *nx, *ny, 1, 1);
   if (p->set_coe_aos(coe, true)) die("solve_elliptic(old)");
+  if (maxnorm) {
+    const int NX = *nx, NY = *ny;
+    double m = 0.0;
+    auto join = [&](T v) { const double a = std::fabs((double)v); m = (m != m) ? m : (a != a) ? a : std::max(m, a); };
+    for (int i = 0; i < NX; ++i) { join(dat[i]); join(dat[(size_t)(NY - 1) * NX + i]); }
+    for (int j = 0; j < NY; ++j) { join(dat[(size_t)j * NX]); join(dat[(size_t)j * NX + NX - 1]); }
+    p->norm_max = 1; p->norm_floor = m;
+  }
   xee_solve_params prm{};
   prm.max_iter = mi; prm.check_step = 100; prm.alpha = (double)*alpha; prm.sync_every = 2;
   prm.detect_explode = 1;   // the legacy isnan tests (:218-240) set err_explode; here: a non-finite residual at a check
-  if (*strategy == 1) { prm.r1 = (double)*strategy_r; prm.r2 = 0.0; prm.converge_time = 1; prm.lost_rate = 5; if (!(prm.r1 > 0)) prm.r1 = 1e-300; }
+  if (absolute) { prm.r1 = (double)*strategy_r; prm.r2 = 0.0; prm.converge_time = 1; prm.lost_rate = 5; if (!(prm.r1 > 0)) prm.r1 = 1e-300; }
   else { prm.r1 = 0.0; prm.r2 = (double)*strategy_r; prm.converge_time = 10; prm.lost_rate = 5; if (!(prm.r2 > 0)) prm.r2 = 1e-300; }
   int iters = 0, e = 0; double r1o = 0, r2o = 0;
   if (p->solve(dat, f, &prm, &iters, &r1o, &r2o, &e, nullptr, true, workspace, *debug == 1 ? 2 : 0)) die("solve_elliptic(old)");

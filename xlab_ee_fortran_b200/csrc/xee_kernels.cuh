@@ -261,21 +261,81 @@ __global__ void init_state_kernel(SolveState<T> st, int nbatch, T r1, T r2, cons
   if (n == 0) *st.active = nbatch;
 }
 
+// max that lets a NaN through (the legacy isnan tests, old-diagnose/xtt-lib/elliptic_tools.f90:218-240, must still see it)
+__device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : (b != b) ? b : (a > b ? a : b); }
+
+constexpr int kResmaxBlocks = 64;
+// Legacy strategies 3/4 (old-diagnose/xtt-lib/elliptic_tools.f90:203-204): err_now = maxval(abs(to_dat)) with to_dat = L psi - f
+// on the interior.  One pass over psi on check sweeps only: partial[n][block] = max |L psi - f| over the block's points, in the
+// same arithmetic as the sweep kernels (the maximum itself is exact in any order).
+template <class T, int ARITH>
+__global__ void __launch_bounds__(256) resmax_kernel(const T* __restrict__ src, const T* __restrict__ f, const T* __restrict__ coe,
+                                                     long long coe_set_stride, long long field_stride, int nx, int ny,
+                                                     const int* __restrict__ done, double* __restrict__ partial) {
+  using R = Rn<T>;
+  __shared__ double red[8];
+  const int n = blockIdx.y;
+  if (done != nullptr && done[n]) return;
+  const size_t nn = (size_t)field_stride;
+  const T* cc = coe + (size_t)n * coe_set_stride;
+  const T* s0 = src + (size_t)n * nn;
+  const T* f0 = f + (size_t)n * nn;
+  const int wi = nx - 2, npts = wi * (ny - 2);
+  double m = 0.0;
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < npts; q += gridDim.x * 256) {
+    const int j = 1 + q / wi, i = 1 + q - (j - 1) * wi;
+    const size_t o = (size_t)j * nx + i;
+    T c[9], p[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = __ldg(cc + k * nn + o);
+    const T* s = s0 + o;
+    p[0] = __ldg(s + nx - 1); p[1] = __ldg(s + nx); p[2] = __ldg(s + nx + 1);
+    p[3] = __ldg(s - 1);      p[4] = __ldg(s);      p[5] = __ldg(s + 1);
+    p[6] = __ldg(s - nx - 1); p[7] = __ldg(s - nx); p[8] = __ldg(s - nx + 1);
+    T r = apply9<T, ARITH>(c, p);
+    const T fv = __ldg(f0 + o);
+    r = (ARITH == XEE_ARITH_STRICT) ? R::sub(r, fv) : r - fv;
+    m = nanmax(m, fabs((double)r));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = nanmax(m, red[w]);
+    partial[(size_t)n * gridDim.x + blockIdx.x] = m;
+  }
+}
+
 // One block per solve: deterministic sum of the tile partials, then the stop-rule state machine.
+// norm_max != 0 (legacy strategies 3/4): the partials are maxima of |r| and err_now = max(they, floor_max), floor_max = the
+// largest |boundary value| (the legacy maxval runs over the whole array, whose rim holds the Dirichlet values).
 template <class T>
 __global__ void __launch_bounds__(128) finalize_check_kernel(SolveState<T> st, const double* __restrict__ partial,
                                                              int ntiles, int ninterior, int cnt, int check_idx,
                                                              int converge_time, int lost_rate, int max_iter,
-                                                             int detect_explode, int stall_checks) {
+                                                             int detect_explode, int stall_checks, int norm_max = 0,
+                                                             double floor_max = 0.0) {
   using R = Rn<T>;
   __shared__ double red[32];
   const int n = blockIdx.x;
   if (st.done[n]) return;
-  double v = 0.0;
-  for (int t = threadIdx.x; t < ntiles; t += 128) v += partial[(size_t)n * ntiles + t];
-  const double tot = block_sum(v, red, threadIdx.x, 4);
+  double v = 0.0, tot;
+  if (norm_max) {
+    for (int t = threadIdx.x; t < ntiles; t += 128) v = nanmax(v, partial[(size_t)n * ntiles + t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int w = 1; w < 4; ++w) v = nanmax(v, red[w]);
+    tot = v;
+  } else {
+    for (int t = threadIdx.x; t < ntiles; t += 128) v += partial[(size_t)n * ntiles + t];
+    tot = block_sum(v, red, threadIdx.x, 4);
+  }
   if (threadIdx.x != 0) return;
-  const T err_now = R::sqrt(R::div((T)tot, (T)ninterior));                        // :199
+  const T err_now = norm_max ? (T)nanmax(tot, floor_max) : R::sqrt(R::div((T)tot, (T)ninterior));   // :199 / legacy :204
   const T err_before = st.err_before[n];
   T ratio = R::div(R::sub(err_before, err_now), err_before);                      // :201
   if (n == 0 && check_idx < st.trace_cap) { st.trace_err[check_idx] = err_now; st.trace_ratio[check_idx] = ratio; }

@@ -151,6 +151,10 @@ struct PlanBase {
   long long kernel_launches = 0;     // launches of the sweep kernel
   int variant_used = 0, depth_used = 1;   // sweep-kernel variant of the last solve/sweeps call (1..5) and its sweeps per pass
   double cheb_rho_used = 0.0, cheb_gamma_used = 1.0;   // Chebyshev parameters of the last accelerated call
+  // residual norm of the stop rule: 0 = RMS over the interior (elliptic_tools.f90:190-199); 1 = max |r|, joined with norm_floor
+  // (legacy strategies 3/4, old-diagnose/xtt-lib/elliptic_tools.f90:203-204; point methods only)
+  int norm_max = 0;
+  double norm_floor = 0.0;
   int rho_subsample = 0;   // > 1 (one operator per solve): probe every rho_subsample-th operator set only and interpolate the
                            // spectral data in between - for series whose operators vary smoothly with the index (set by the caller)
 };
@@ -165,6 +169,7 @@ struct Plan : PlanBase {
   T* io_f = nullptr;
   SolveState<T> st{};
   double* partial = nullptr;
+  double* partial_max = nullptr;   // [nbatch][kResmaxBlocks] (norm_max only)
   int ntiles = 0, gx = 0, gy = 0, gz = 0, spb = 1;
   int* h_active = nullptr;  // pinned
   cudaStream_t own_stream = nullptr;
@@ -440,7 +445,7 @@ struct Plan : PlanBase {
     { TraceTimer t("  ~Plan: field buffers"); pool_free(coe); pool_free(linefac); pool_free(linepack); pool_free(tl_ainv); pool_free(tl_tmp); pool_free(tl_part); pool_free(tl_rc); pool_free(tl_ck); pool_free(tl_cv); pool_free(tl_scale); pool_free(tl_band); pool_free(x1); pool_free(x2); pool_free(x3); pool_free(io_psi); pool_free(io_f); pool_free(rho_dev);
       pool_free(res_omega); pool_free(res_final); pool_free(res_prev); pool_free(res_halo); pool_free(res_ints); pool_free(res_partial); }
     { TraceTimer t("  ~Plan: small cudaFree");
-      pool_free(partial);
+      pool_free(partial); pool_free(partial_max);
       pool_free(st.done); pool_free(st.iters); pool_free(st.ccnt); pool_free(st.lcnt); pool_free(st.errb);
       pool_free(st.err_before); pool_free(st.err_now); pool_free(st.ratio); pool_free(st.r1); pool_free(st.r2);
       pool_free(st.active); pool_free(st.trace_err); pool_free(st.trace_ratio); pool_free(st.best_err); pool_free(st.stall); }
@@ -1277,7 +1282,9 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
   XEE_LAUNCH_OK();
   // v3: the whole loop in one cooperative launch (single / few solves that fit on the chip)
   int want_kernel = d.kernel > 0 ? d.kernel : env_int("XEE_KERNEL", 0);
-  const bool resident_ok = !use_line && (d.shared_coe || nb == 1) && max_iter >= 1 && resident_fits();
+  if (norm_max && (use_line || use_tb)) return fail("xee: the max-abs residual norm (legacy strategies 3/4) is provided for the point methods only");
+  if (norm_max && !partial_max) XEE_CHECK(pool_alloc(&partial_max, sizeof(double) * nb * kResmaxBlocks));
+  const bool resident_ok = !norm_max && !use_line && (d.shared_coe || nb == 1) && max_iter >= 1 && resident_fits();
   if (want_kernel == 3 && !resident_ok) return fail("xee: kernel=3 (resident) needs a problem that fits: nbatch*strips <= SMs, <= 1536 points per strip");
   if (want_kernel == 3 || (want_kernel == 0 && resident_ok && nb <= 2)) {
     cudaEvent_t e0 = next_event(), e1 = next_event();
@@ -1358,8 +1365,18 @@ int Plan<T>::solve(void* psi, const void* f, const xee_solve_params* prm, int* i
     XEE_CHECK(cudaEventRecord(e1, s));
     if ((cnt % check_step) == 0) {
       // an accelerated iteration with a wrong spectral estimate diverges: a non-finite residual always stops it (err bit 1)
-      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, partial, use_tb ? tb_ntiles() : sweep_ntiles(), ninterior, cnt, check_idx, converge_time,
-                                                  lost_rate, max_iter, prm->detect_explode || mode == MODE_CHEBYSHEV, prm->stall_checks);
+      if (norm_max) {   // the residual of the iterate this check sweep read (it is still in its buffer), in the max norm
+        const T* src = (cnt & 1) ? x0 : x1;
+        const dim3 g(kResmaxBlocks, nb);
+        if (d.arith == XEE_ARITH_STRICT)
+          resmax_kernel<T, XEE_ARITH_STRICT><<<g, 256, 0, s>>>(src, fd, coe, d.shared_coe ? 0 : (long long)kPlanes * nn, (long long)nn, d.nx, d.ny, st.done, partial_max);
+        else
+          resmax_kernel<T, XEE_ARITH_FAST><<<g, 256, 0, s>>>(src, fd, coe, d.shared_coe ? 0 : (long long)kPlanes * nn, (long long)nn, d.nx, d.ny, st.done, partial_max);
+        XEE_LAUNCH_OK();
+      }
+      finalize_check_kernel<T><<<nb, 128, 0, s>>>(st, norm_max ? partial_max : partial, norm_max ? kResmaxBlocks : use_tb ? tb_ntiles() : sweep_ntiles(),
+                                                  ninterior, cnt, check_idx, converge_time, lost_rate, max_iter,
+                                                  prm->detect_explode || mode == MODE_CHEBYSHEV, prm->stall_checks, norm_max, norm_floor);
       XEE_LAUNCH_OK();
       const int slot = check_idx & 3;
       XEE_CHECK(cudaMemcpyAsync(&h_active[slot], st.active, sizeof(int), cudaMemcpyDeviceToHost, s));
