@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     if (w == 3) CK(cudaEventRecord(e0));
     const int src = w & 1;
     A.dst = x[src ^ 1];
-    kern<<<grid, ln::NT, smem>>>(A, mxh[src], mxp[src ^ 1], mf, mo[src ^ 1]);
+    kern<<<grid, ln::NT, smem>>>(A, mxh[src], mxp[src ^ 1], mf, mo[src ^ 1], mf);
   }
   CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

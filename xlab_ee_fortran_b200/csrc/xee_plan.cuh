@@ -532,6 +532,12 @@ struct Plan : PlanBase {
   double* two_cv(int slot, int nb) const { return tl_cv + (size_t)slot * nb * tld.pz * tld.px; }
   int two_coarse(int slot, int nb, double scale, const T* rho_ps_dev, int cheb_k, const int* done, cudaStream_t s) {
     const int nt = ln_tiles_x * ln_tiles_y;
+    if (d.shared_coe && nb <= 4 && !rho_ps_dev && tld.nc <= tl::kMaxNcSmem) {   // single solves, probes: one launch instead of two
+      tl::coarse_gather_matvec_kernel<<<dim3((tld.nc + 7) / 8, nb), 256, 0, s>>>(tl_ainv, tl_part, two_cv(slot, d.nbatch), done, scale, nt, ln_tiles_x,
+                                                                              ln_tiles_y, tld.nc, tld.ncp, tld.ncx, tld.px, tld.pz * tld.px);
+      XEE_LAUNCH_OK();
+      return 0;
+    }
     tl::coarse_gather_kernel<<<nb, 256, 0, s>>>(tl_part, tl_rc, done, nt, ln_tiles_x, ln_tiles_y, tld.ncx, tld.ncz, tld.ncp);
     XEE_LAUNCH_OK();
     if (!d.shared_coe || nb <= 4) {

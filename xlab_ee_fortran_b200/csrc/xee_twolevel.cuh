@@ -163,31 +163,32 @@ static __global__ void __launch_bounds__(128) band_inverse_kernel(const double* 
 // kinds 0/1 = sum_j (1 - j/16) S0/S1 -> coarse row of the tile's first row, 2/3 = sum_j (j/16) S0/S1 -> the next coarse row.
 // A segment s (8 points from i = 8 s) lies in radial cell c = s / 2 at offset o0 = 8 (s & 1): its weight sum towards the cell's
 // right node is (o0 S0 + S1)/16, towards its left node S0 minus that.
+__device__ __forceinline__ double gather_node(const double* __restrict__ pn, int idx, int tiles_x, int tiles_y, int ncx) {
+  const int nsegs = tiles_x * 8;
+  const int p = idx % ncx + 1, q = idx / ncx + 1;
+  double tot = 0.0;
+#pragma unroll
+  for (int zc = 0; zc < 2; ++zc) {            // z-cell q-1 (kinds 2,3) then z-cell q (kinds 0,1)
+    const int ty = q - 1 + zc, kb = zc == 0 ? 2 : 0;
+    if (ty < 0 || ty >= tiles_y) continue;
+#pragma unroll
+    for (int ss = 0; ss < 4; ++ss) {          // segments 2p-2, 2p-1 (left cell), 2p, 2p+1 (right cell)
+      const int s = 2 * p - 2 + ss;
+      if (s < 0 || s >= nsegs) continue;
+      const double* t = pn + (size_t)(ty * tiles_x + s / 8) * 32 + (s & 7);
+      const double s0 = t[kb * 8], s1 = t[(kb + 1) * 8];
+      const double right = ((double)(8 * (s & 1)) * s0 + s1) * (1.0 / HR);
+      tot += ss < 2 ? right : s0 - right;
+    }
+  }
+  return tot;
+}
 static __global__ void coarse_gather_kernel(const double* __restrict__ part, double* __restrict__ Rc, const int* __restrict__ done,
                                      int ntiles, int tiles_x, int tiles_y, int ncx, int ncz, int ncp) {
   const int n = blockIdx.x;
   if (done && done[n]) return;
   const double* pn = part + (size_t)n * ntiles * 32;
-  const int nsegs = tiles_x * 8;
-  for (int idx = threadIdx.x; idx < ncx * ncz; idx += blockDim.x) {
-    const int p = idx % ncx + 1, q = idx / ncx + 1;
-    double tot = 0.0;
-#pragma unroll
-    for (int zc = 0; zc < 2; ++zc) {            // z-cell q-1 (kinds 2,3) then z-cell q (kinds 0,1)
-      const int ty = q - 1 + zc, kb = zc == 0 ? 2 : 0;
-      if (ty < 0 || ty >= tiles_y) continue;
-#pragma unroll
-      for (int ss = 0; ss < 4; ++ss) {          // segments 2p-2, 2p-1 (left cell), 2p, 2p+1 (right cell)
-        const int s = 2 * p - 2 + ss;
-        if (s < 0 || s >= nsegs) continue;
-        const double* t = pn + (size_t)(ty * tiles_x + s / 8) * 32 + (s & 7);
-        const double s0 = t[kb * 8], s1 = t[(kb + 1) * 8];
-        const double right = ((double)(8 * (s & 1)) * s0 + s1) * (1.0 / HR);
-        tot += ss < 2 ? right : s0 - right;
-      }
-    }
-    Rc[(size_t)n * ncp + idx] = tot;
-  }
+  for (int idx = threadIdx.x; idx < ncx * ncz; idx += blockDim.x) Rc[(size_t)n * ncp + idx] = gather_node(pn, idx, tiles_x, tiles_y, ncx);
 }
 
 // Cv[n] = scale * Ainv Rc[n] for the whole batch: C[i][n] = sum_k Ainv[i][k] Rc[n][k], one small fp64 GEMM (ncp x nbatch x ncp)
@@ -260,10 +261,47 @@ static __global__ void __launch_bounds__(256) coarse_matvec_kernel(const double*
   if (i >= nc || (done && done[n])) return;
   const double* ar = Ainv + (size_t)n * ainv_stride + (size_t)i * ncp; const double* rc = Rc + (size_t)n * ncp;
   double t = 0.0;
-  for (int k = lane; k < ncp; k += 32) t = fma(ar[k], rc[k], t);
+  for (int k0 = lane; k0 < ncp; k0 += 256) {     // all loads of a step in flight before the sum (same order as a plain loop)
+    double av[8], rv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const bool in = k0 + 32 * q < ncp; av[q] = in ? __ldg(ar + k0 + 32 * q) : 0.0; rv[q] = in ? __ldg(rc + k0 + 32 * q) : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t = fma(av[q], rv[q], t);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (lane == 0) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = (scale_ps ? scale_ps[n] : scale) * t;
+}
+// Gather and product in one launch for a handful of solves with a shared operator (single solves, the spectral probes: every
+// kernel of such a sweep is latency, not work): every block first forms the whole P^T r of its solve in shared memory (the same
+// sums in the same order as coarse_gather_kernel), then its 8 rows of the product.
+constexpr int kMaxNcSmem = 2048;
+static __global__ void __launch_bounds__(256) coarse_gather_matvec_kernel(const double* __restrict__ Ainv, const double* __restrict__ part,
+                                                                          double* __restrict__ Cv, const int* __restrict__ done, double scale,
+                                                                          int ntiles, int tiles_x, int tiles_y, int nc, int ncp, int ncx,
+                                                                          int px, int pzpx) {
+  __shared__ double rc[kMaxNcSmem];
+  const int n = blockIdx.y;
+  if (done && done[n]) return;
+  const double* pn = part + (size_t)n * ntiles * 32;
+  for (int idx = threadIdx.x; idx < nc; idx += 256) rc[idx] = gather_node(pn, idx, tiles_x, tiles_y, ncx);
+  __syncthreads();
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= nc) return;
+  const double* ar = Ainv + (size_t)i * ncp;
+  double t = 0.0;
+  // (ncp is a multiple of 64; Rc is zero-padded to it.)  The row comes from L2: all loads of a step are issued before the sum,
+  // which keeps its order
+  for (int k0 = lane; k0 < ncp; k0 += 256) {
+    double av[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) av[q] = k0 + 32 * q < ncp ? __ldg(ar + k0 + 32 * q) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int k = k0 + 32 * q; t = fma(av[q], k < nc ? rc[k] : 0.0, t); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) Cv[(size_t)n * pzpx + (size_t)(i / ncx + 1) * px + (i % ncx + 1) + COL0] = scale * t;
 }
 // per-solve factor of the coarse correction, -omega_k(rho_n) gamma (one operator per solve: the sweep kernel computes the same
 // omega from the same rho)
