@@ -220,6 +220,29 @@ __global__ void __launch_bounds__(kDirBX* kDirBY) sweep_direct_kernel(const Swee
   }
 }
 
+// Start vectors of the spectral probes (estimate_rho), for every operator set at once (grid.y = sets): kind 0 = the lowest sine
+// mode sin(pi i/(nx-1)) sin(pi j/(ny-1)); kind 1 = the same, alternating in z and modulated (rough: for the largest eigenvalue
+// of the two-level operator).  Zero on the boundary.  (Generated on the host and uploaded set by set until round 2: 4 ms of
+// libm and pageable copies per probe.)
+template <class T>
+__global__ void probe_start_kernel(T* __restrict__ e, int nx, int ny, long long nn, int kind) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nx * ny) return;
+  const int j = q / nx, i = q - j * nx;
+  double v = 0.0;
+  if (i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1) {
+    v = sin(M_PI * i / (nx - 1)) * sin(M_PI * j / (ny - 1));
+    if (kind == 1) v = (double)(T)v * (double)((T)((j & 1) ? -1.0 : 1.0) * (T)(1.0 + 0.25 * sin(0.7 * i + 1.3 * j)));
+  }
+  e[(size_t)blockIdx.y * nn + q] = (T)v;
+}
+// set 0 of a probe vector copied to the sets 1 .. gridDim.y
+template <class T>
+__global__ void probe_replicate_kernel(T* __restrict__ e, long long nn) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nn) e[(size_t)(blockIdx.y + 1) * nn + q] = e[q];
+}
+
 // D-weighted norm per solve, sum |coe5| x^2, for the spectral-radius probes: kWnormParts blocks per solve write partial sums
 // (a single block per solve took 150 us for one 512x256 field: pure latency); the host adds them in a fixed order.
 constexpr int kWnormParts = 32;

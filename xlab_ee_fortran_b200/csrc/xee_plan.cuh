@@ -938,12 +938,13 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   XEE_CHECK(pool_alloc(&zf, sizeof(T) * nn * ns)); XEE_CHECK(pool_alloc(&nrm_d, sizeof(double) * ns * kWnormParts));
   if (!rho_dev) XEE_CHECK(pool_alloc(&rho_dev, sizeof(T) * ns));
   XEE_CHECK(cudaMemsetAsync(zf, 0, sizeof(T) * nn * ns, s));
-  std::vector<T> h(nn, T(0));
-  for (int j = 1; j < d.ny - 1; ++j)
-    for (int i = 1; i < d.nx - 1; ++i)
-      h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
-  for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-  XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+  auto start_vector = [&](int kind) -> int {     // e0 = e1 = start vector of `kind` (probe_start_kernel) in every set
+    probe_start_kernel<T><<<dim3((unsigned)((nn + 255) / 256), ns), 256, 0, s>>>(e0, d.nx, d.ny, (long long)nn, kind);
+    XEE_LAUNCH_OK();
+    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  };
+  if (start_vector(0)) return 1;
   // probe launch geometry: `ns` solves through the direct kernel
   d.nbatch = ns; spb = 1; gz = ns;
   std::vector<double> nA(ns), nB(ns), rho(ns, 0.0);
@@ -990,10 +991,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     // pushes an isolated eigenvalue above 2 (such a mode separates quickly).  Over-estimating lmax by 2 % costs 1 % in sweeps.
     // lmin: the estimator below on G with the provisional step gamma0 = 1 / lmax, whose spectrum [0, 1 - lmin/lmax] is
     // non-negative, so its dominant mode is the smooth one the probes look for.
-    for (int j = 1; j < d.ny - 1; ++j)
-      for (int i = 1; i < d.nx - 1; ++i) h[(size_t)j * d.nx + i] *= (T)((j & 1) ? -1.0 : 1.0) * (T)(1.0 + 0.25 * std::sin(0.7 * i + 1.3 * j));
-    for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+    if (start_vector(1)) return 1;
     tl_gamma = 1.0;
     const int itL = env_int("XEE_LMAX_ITERS", ns > 1 ? 24 : 60);
     for (int k = 1; k <= itL && !rc; ++k) {
@@ -1016,11 +1014,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     }
     tl_gamma = 1.0 / tl_lmax;
     // restore the smooth start vector of stage A
-    for (int j = 1; j < d.ny - 1; ++j)
-      for (int i = 1; i < d.nx - 1; ++i)
-        h[(size_t)j * d.nx + i] = (T)(std::sin(M_PI * i / (d.nx - 1)) * std::sin(M_PI * j / (d.ny - 1)));
-    for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
-    XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
+    if (start_vector(0)) return 1;
     parity = 0;
   }
   // ---- stage A
@@ -1102,13 +1096,15 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   if (use_line && env_int("XEE_RHO_ELLIPSE", 1)) {
     const int pc = env_int("XEE_RHO_PROBE_C", 64), roundsC = 3;
     uint32_t lcg = 12345u;
+    std::vector<T> h(nn, T(0));
     for (int j = 1; j < d.ny - 1; ++j)
       for (int i = 1; i < d.nx - 1; ++i) { lcg = lcg * 1664525u + 1013904223u; h[(size_t)j * d.nx + i] = (T)((double)(lcg >> 8) / 8388608.0 - 1.0); }
     std::vector<char> doneC(ns, 0);
     for (int r = 0; r < roundsC && !rc; ++r) {
       for (int n = 0; n < ns; ++n) rho_h[n] = (T)foci[n];
       XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
-      for (int n = 0; n < ns; ++n) XEE_CHECK(cudaMemcpyAsync(e0 + (size_t)n * nn, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));
+      XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));      // one upload, replicated on the device
+      if (ns > 1) { probe_replicate_kernel<T><<<dim3((unsigned)((nn + 255) / 256), ns - 1), 256, 0, s>>>(e0, (long long)nn); XEE_LAUNCH_OK(); }
       XEE_CHECK(cudaMemcpyAsync(e1, e0, sizeof(T) * nn * ns, cudaMemcpyDeviceToDevice, s));
       if (use_two && two_reset(ns, s)) return 1;
       parity = 0;
