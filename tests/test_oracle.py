@@ -297,3 +297,40 @@ def test_integral_check_identity_of_the_legacy_driver():
     assert np.all(tab[:, 2] == 0)
     assert np.allclose(tab[:, 7], tab[:, 5], rtol=2e-2)
     assert np.all(tab[:2, 5] > 1e-3)            # heating inside the vortex core is the efficient one
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("strategy,sr", [(1, 1e-3), (2, 0.3)])
+def test_legacy_loop_restatement_agrees_with_the_mapped_current_solver(dt, strategy, sr):
+    """Two independent restatements of the legacy stop rules (src/old-diagnose/xtt-lib/elliptic_tools.f90:168-300): the literal
+    loop in tests/legacy_oracle.py and the mapping onto the current solver's criteria (strategy 1 = r1 only, converge_time 1;
+    strategy 2 = r2 only, converge_time 10, lost_rate 5) that the drop-in uses.  Same sweeps, same field bit for bit."""
+    from tests import legacy_oracle as L
+    rng = np.random.default_rng(31)
+    nx, ny = 48, 36
+    a = (1.0 + rng.random((ny - 2, nx - 1))).astype(dt); c = (1.0 + rng.random((ny - 1, nx - 2))).astype(dt)
+    b = (0.05 * rng.standard_normal((ny - 1, nx - 1))).astype(dt)
+    f = rng.standard_normal((ny, nx)).astype(dt); x0 = rng.standard_normal((ny, nx)).astype(dt)
+    x0[0] = 0; x0[-1] = 0; x0[:, 0] = 0; x0[:, -1] = 0
+    coe, _ = O.cal_coe(a, b, c, 1.0, 0.5, nx, ny)
+    loop = L.old_solve_loop(strategy, sr, 3000, 0.9, x0, coe, f)
+    dat, used, r = L.old_solve(strategy, sr, 3000, 0.9, x0, coe, f)
+    assert 0 < loop["strategy"] < 3000 and loop["strategy"] == used and loop["err"] == 0
+    assert np.array_equal(loop["dat"], dat)
+    assert loop["strategy_r"] == pytest.approx(r, rel=1e-12 if dt is np.float64 else 1e-6)
+
+
+def test_legacy_loop_max_norm_sees_the_dirichlet_rim():
+    """Strategies 3 / 4 take maxval(abs(to_dat)) over the whole array (:203-204): with a non-zero boundary the norm never drops
+    below the largest boundary value, so strategy 3 runs to max_iter and strategy 4 stops after its ten constant checks."""
+    from tests import legacy_oracle as L
+    rng = np.random.default_rng(5)
+    nx, ny = 24, 20
+    a = (1.0 + rng.random((ny - 2, nx - 1))); c = (1.0 + rng.random((ny - 1, nx - 2))); b = np.zeros((ny - 1, nx - 1))
+    f = rng.standard_normal((ny, nx)); x0 = rng.standard_normal((ny, nx))
+    rim = max(np.abs(x0[0]).max(), np.abs(x0[-1]).max(), np.abs(x0[:, 0]).max(), np.abs(x0[:, -1]).max())
+    coe, _ = O.cal_coe(a, b, c, 1.0, 1.0, nx, ny)
+    r3 = L.old_solve_loop(3, 1e-3, 2000, 1.0, x0, coe, f)
+    assert r3["strategy"] == 2000 and r3["err"] == 1 and r3["strategy_r"] == rim
+    r4 = L.old_solve_loop(4, 0.05, 3000, 1.0, x0, coe, f)
+    assert r4["err"] == 0 and r4["strategy_r"] == rim and r4["strategy"] % 100 == 0
