@@ -991,6 +991,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
     // pushes an isolated eigenvalue above 2 (such a mode separates quickly).  Over-estimating lmax by 2 % costs 1 % in sweeps.
     // lmin: the estimator below on G with the provisional step gamma0 = 1 / lmax, whose spectrum [0, 1 - lmin/lmax] is
     // non-negative, so its dominant mode is the smooth one the probes look for.
+    TraceTimer t1("  probe: largest eigenvalue");
     if (start_vector(1)) return 1;
     tl_gamma = 1.0;
     const int itL = env_int("XEE_LMAX_ITERS", ns > 1 ? 24 : 60);
@@ -1021,11 +1022,13 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   // probe lengths: the block-line splitting has a ~20x larger spectral gap than point Jacobi, so its modes separate in
   // proportionally fewer sweeps (64/64 measured: same sweep counts to tolerance as 200/200; 32/32 costs 2-3 % more sweeps)
   const int itA = env_int("XEE_RHO_ITERS", use_two ? 32 : use_line ? 64 : 200);
+  { TraceTimer t2("  probe: stage A");
   for (int k = 1; k <= itA && !rc; ++k) {
     rc = sweep(MODE_JACOBI, 1);
     if (k >= itA - 1) rc = rc || flush();
     if (k == itA - 1) rc = rc || norms(parity ? e1 : e0, nA);
     if (k == itA) rc = rc || norms(parity ? e1 : e0, nB);
+  }
   }
   for (int n = 0; n < ns && !rc; ++n) {
     rho[n] = nA[n] > 0 ? nB[n] / nA[n] : 0.0;
@@ -1041,6 +1044,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
   std::vector<char> settled(ns, 0);
   auto lncosh = [](double x) { return x + std::log1p(std::exp(-2.0 * x)) - M_LN2; };
   for (int r = 0; r < rounds && !rc; ++r) {
+    TraceTimer t3("  probe: stage B round");
     for (int n = 0; n < ns; ++n) rho_h[n] = (T)rho[n];
     XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
     // restart the Chebyshev sequence from the current iterate: x_{-1} := x_0
@@ -1068,6 +1072,11 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
       const double rel = std::fabs(rho_new - rE) / (1.0 - rE);
       rho[n] = rho_new;
       if (rel < 0.02) settled[n] = 1; else all_settled = false;
+    }
+    if (env_int("XEE_TRACE", 0)) {
+      double worst = 0.0;
+      for (int n = 0; n < ns; ++n) worst = std::max(worst, std::fabs(rho[n] - (double)rho_h[n]) / (1.0 - (double)rho_h[n]));
+      fprintf(stderr, "xee: stage B round %d: 1 - rho[0] = %.4e, largest relative change of the gap %.3f\n", r, 1.0 - rho[0], worst);
     }
     if (all_settled) break;
   }
@@ -1101,6 +1110,7 @@ int Plan<T>::estimate_rho(cudaStream_t s) {
       for (int i = 1; i < d.nx - 1; ++i) { lcg = lcg * 1664525u + 1013904223u; h[(size_t)j * d.nx + i] = (T)((double)(lcg >> 8) / 8388608.0 - 1.0); }
     std::vector<char> doneC(ns, 0);
     for (int r = 0; r < roundsC && !rc; ++r) {
+      TraceTimer t4("  probe: stage C round");
       for (int n = 0; n < ns; ++n) rho_h[n] = (T)foci[n];
       XEE_CHECK(cudaMemcpyAsync(rho_dev, rho_h.data(), sizeof(T) * ns, cudaMemcpyHostToDevice, s));
       XEE_CHECK(cudaMemcpyAsync(e0, h.data(), sizeof(T) * nn, cudaMemcpyHostToDevice, s));      // one upload, replicated on the device
