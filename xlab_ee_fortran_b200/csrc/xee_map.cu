@@ -118,8 +118,7 @@ struct Map : MapBase {
     const int nr = d.nr, nz = d.nz, nb = d.nheat;
     if (!s) s = pl->own_stream;
     XEE_CHECK(cudaMemcpyAsync(heat_d, heat, sizeof(Heat) * nb, heat_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    dim3 gf((nr + 127) / 128, nz, nb);
-    heating_rhs_kernel<T><<<gf, 128, 0, s>>>(heat_d, f, ra, za, ex, nr, nz, k.g0, k.theta0, k.Cp); XEE_LAUNCH_OK();
+    heating_rhs_kernel<T><<<heating_rhs_grid(nr, nz, nb), dim3(kHeatBX, kHeatBY), 0, s>>>(heat_d, f, ra, za, ex, nr, nz, k.g0, k.theta0, k.Cp); XEE_LAUNCH_OK();
     XEE_CHECK(cudaMemsetAsync(psi, 0, sizeof(T) * nn * nb, s));     // rpsi = 0: boundary condition and first guess
     xee_solve_params prm = *prm_in;
     if (d.r1_rel_rms_f > 0) {   // tolerance relative to each location's own forcing: r1_n = r1_rel * rms(f_n)

@@ -209,7 +209,7 @@ struct Series : SeriesBase {
     XEE_CHECK(cudaStreamSynchronize(s));
     if (pl->set_abc(a, b, c, (double)dr, (double)dz)) return 1;
     background_theta_kernel<T><<<nb, 256, 0, s>>>(A, B, theta, ra, za, nr, nz, k.g0, k.theta0); XEE_LAUNCH_OK();
-    heating_rhs_kernel<T><<<gO, 128, 0, s>>>(heat, f, ra, za, ex, nr, nz, k.g0, k.theta0, k.Cp); XEE_LAUNCH_OK();
+    heating_rhs_kernel<T><<<heating_rhs_grid(nr, nz, nb), dim3(kHeatBX, kHeatBY), 0, s>>>(heat, f, ra, za, ex, nr, nz, k.g0, k.theta0, k.Cp); XEE_LAUNCH_OK();
     dim3 gm((nz - 1 + 63) / 64, nb);
     series_m2_kernel<T><<<gm, 64, 0, s>>>(C, m2, ra, ra, nr, nz, nb); XEE_LAUNCH_OK();
     series_mom_rhs_kernel<T><<<gO, 128, 0, s>>>(snaps, m2, f, ra, ra, za, nr, nz); XEE_LAUNCH_OK();
